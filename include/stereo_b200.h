@@ -1,0 +1,154 @@
+/* stereo_b200.h — C ABI of the B200-native stereo-matching hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json names: the reference's
+ * CStereoMatching (NCC matching, constraint filters, rematch, median, refinement) and the
+ * per-point triangulation DisparityToCloud.  The reference has no FFI; its boundary is the C++
+ * class surface.  Every entry point below cites the reference code it replaces,
+ * all paths relative to /root/reference/reconstruction/.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every call returns an sb200 status
+ * (0 = OK); one context per GPU and per host thread; no global state.  All host buffers are
+ * caller-owned, C-contiguous, reference layout: images are interleaved BGR u8 rows of 3*W bytes
+ * (cv::Mat CV_8UC3), masks u8 rows of W bytes, disparity maps row-major s16 or f64 (cv::Mat
+ * CV_16S / CV_64F, the two types MatchOneLayer alternates between).
+ *
+ * There is NO CPU fallback behind this ABI: a machine without a CUDA device gets
+ * SB200_ERR_NO_DEVICE from sb200_ctx_create and nothing else works.
+ */
+#ifndef STEREO_B200_H
+#define STEREO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SB200_API __attribute__((visibility("default")))
+#else
+#define SB200_API
+#endif
+
+#define SB200_NOMATCH (-10000) /* CStereoMatching.h:9 */
+
+enum sb200_status {
+  SB200_OK = 0,
+  SB200_ERR_NO_DEVICE = 1,        /* no CUDA device / wrong architecture */
+  SB200_ERR_BAD_ARG = 2,
+  SB200_ERR_CUDA = 3,             /* a CUDA call failed; sb200_last_error() has the text */
+  SB200_ERR_STATE = 4,            /* call order violated (e.g. match before upload) */
+  SB200_ERR_DEGENERATE_MARGIN = 5 /* the reference exit(0)s here: CStereoMatching.cpp:827-830,954-958 */
+};
+
+/* Stage ids of MatchOneLayer, CStereoMatching.cpp:51-109 (same numbering as SURVEY.md §3.3). */
+enum sb200_stage {
+  SB200_STAGE_FIND_MARGIN = 1,   /* :51-52   FindMargin x2                          */
+  SB200_STAGE_INITIAL_MATCH = 2, /* :53-62   Lowest/HighLevelInitialMatch x2        */
+  SB200_STAGE_SMOOTH = 3,        /* :66-67   SmoothConstraint x2                    */
+  SB200_STAGE_ORDER = 4,         /* :71-72   OrderConstraint x2                     */
+  SB200_STAGE_UNIQUE_1 = 5,      /* :75      UniquenessContraint<short>             */
+  SB200_STAGE_REMATCH = 6,       /* :80-81   Rematch x2 (SetBoundary_smooth + NCC)  */
+  SB200_STAGE_UNIQUE_2 = 7,      /* :86      UniquenessContraint<short>             */
+  SB200_STAGE_MEDIAN = 8,        /* :89-90   MedianFilter x2                        */
+  SB200_STAGE_REFINE = 9,        /* :95-98   DisparityRefine x2                     */
+  SB200_STAGE_UNIQUE_3 = 10      /* :109     UniquenessContraint<double>            */
+};
+
+/* Boundary, CManageData.h:10-14 (same field order as the reference struct). */
+typedef struct sb200_boundary {
+  int32_t YL, YR, XL, XR, width, height;
+} sb200_boundary;
+
+typedef struct sb200_ctx sb200_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------
+ * Replaces CStereoMatching::Init (CStereoMatching.cpp:5-13: radii, ws, disparity_offset) plus the
+ * sizes CManageData::Init reads from config.yml (CManageData.cpp:26-42: PyrmNum, LowestLevelWidth/
+ * Height) and m_OriginSize (CManageData.cpp:68-69), which sets the triangulation scale
+ * (CStereoMatching.cpp:692).  Allocates every device buffer for one camera pair once. */
+SB200_API int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, int lowest_h, int origin_w,
+                     int origin_h, int radius, double ws, int offset);
+SB200_API void sb200_ctx_destroy(sb200_ctx* ctx);
+SB200_API const char* sb200_last_error(const sb200_ctx* ctx);
+SB200_API const char* sb200_status_string(int status);
+
+/* ---- staging a pair ----------------------------------------------------------------------------
+ * What CStereoMatching::Rectify leaves in cam[pair][k].image / .mask (CStereoMatching.cpp:154-158)
+ * for the two views, at the top pyramid level (lowest << (pyrm_num-1)).  The call copies them to
+ * HBM and runs ConstructPyrm (:1040-1053, pyrDown of image and mask per level) and FindMargin for
+ * every level on the device.  Host buffers may be pageable or pinned. */
+SB200_API int sb200_pair_upload(sb200_ctx* ctx, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0,
+                      const uint8_t* mask1);
+/* Q (4x4, AFTER the sign flip at :138), R_final (3x3, :132), T_final (3, :133), row-major f64. */
+SB200_API int sb200_pair_set_calib(sb200_ctx* ctx, const double* Q, const double* R_final, const double* T_final);
+
+/* ---- the hot path ------------------------------------------------------------------------------
+ * MatchAllLayer's per-pair body, CStereoMatching.cpp:21-29: MatchOneLayer for every level
+ * (stages 1-10) then DisparityToCloud.  Asynchronous work is finished when the call returns.
+ * n_points receives the number of emitted 3-D points. */
+SB200_API int sb200_match_pair(sb200_ctx* ctx, int64_t* n_points);
+/* MatchOneLayer(disparity, level), CStereoMatching.cpp:36-113. */
+SB200_API int sb200_match_one_layer(sb200_ctx* ctx, int level);
+/* One stage of MatchOneLayer (the reference's SaveMat dump points, :63-111) — parity hook. */
+SB200_API int sb200_run_stage(sb200_ctx* ctx, int level, int stage);
+/* DisparityRefine normally runs 30+30*level sweeps (:95); n >= 0 overrides, n < 0 restores. */
+SB200_API int sb200_set_refine_iters(sb200_ctx* ctx, int n);
+
+/* ---- disparity maps (cv::Mat disparity[2] of MatchAllLayer, :22) --------------------------------
+ * elem_size is 2 (s16, stages 2-8) or 8 (f64, stages 9-10), 0 before the first match. */
+SB200_API int sb200_disparity_info(const sb200_ctx* ctx, int* width, int* height, int* elem_size);
+SB200_API int sb200_get_disparity(sb200_ctx* ctx, int dir, void* host_out);
+/* Teacher forcing for stage-by-stage parity: replace disparity[dir] (both dirs must share a type). */
+SB200_API int sb200_set_disparity(sb200_ctx* ctx, int dir, const void* host_in, int width, int height, int elem_size);
+/* BL / BR of SetBoundary_smooth (CStereoMatching.cpp:817-942), the commented bl.dat dump (:515). */
+SB200_API int sb200_get_rematch_bounds(sb200_ctx* ctx, int dir, int16_t* bl_out, int16_t* br_out);
+
+/* ---- pyramid and margins ------------------------------------------------------------------------
+ * imagePyrm[level][view] / maskPyrm[level][view] (CManageData.h) and `margin[view]` at `level`
+ * (FindMargin, CStereoMatching.cpp:1011-1038).  Either output pointer may be NULL. */
+SB200_API int sb200_get_level(sb200_ctx* ctx, int level, int view, uint8_t* bgr_out, uint8_t* mask_out);
+SB200_API int sb200_get_margin(const sb200_ctx* ctx, int level, int view, sb200_boundary* out);
+
+/* ---- triangulation ------------------------------------------------------------------------------
+ * DisparityToCloud<double>(disparity[0], maskPyrm[L-1][0], Q, L-1, true, pair), :682-761: one point
+ * per masked, matched pixel of view 0 in row-major order — the sequence of InsertPoint calls (:751).
+ * xyz is what InsertPoint receives (f64), bgr the three source bytes the PLY branch writes
+ * (:754-756), pix the flat index y*W+x of the source pixel.  Any output pointer may be NULL. */
+SB200_API int sb200_triangulate(sb200_ctx* ctx, int64_t* n_points);
+SB200_API int sb200_get_points(sb200_ctx* ctx, double* xyz_out, uint8_t* bgr_out, int32_t* pix_out);
+/* Device-resident point buffers of the last triangulation, for the per-pair all-gather over NCCL
+ * (SURVEY.md §8e); valid until the next sb200_triangulate / sb200_match_pair on this context. */
+SB200_API int sb200_points_device(sb200_ctx* ctx, void** xyz_dev, void** bgr_dev, void** pix_dev, int64_t* n_points);
+
+/* ---- one-call host-buffer entry (what the C++ CStereoMatching::MatchAllLayer mirror calls) ------
+ * upload + set_calib + match_pair + download of the points, H2D/D2H included.  xyz_out/bgr_out/
+ * pix_out must hold capacity points; returns SB200_ERR_BAD_ARG if more are produced. */
+SB200_API int sb200_match_pair_host(sb200_ctx* ctx, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0,
+                          const uint8_t* mask1, const double* Q, const double* R_final, const double* T_final,
+                          double* xyz_out, uint8_t* bgr_out, int32_t* pix_out, int64_t capacity,
+                          int64_t* n_points);
+
+/* ---- instrumentation ----------------------------------------------------------------------------
+ * The stream all kernels of this context are launched on (a cudaStream_t), so callers can time
+ * with CUDA events on the launching stream. */
+SB200_API void* sb200_stream(sb200_ctx* ctx);
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+SB200_API int64_t sb200_launch_count(const sb200_ctx* ctx);
+/* Accumulated device time (ms, CUDA events) per stage id 0..15 since the last reset; index 0 is the
+ * pyramid build, 1-10 the MatchOneLayer stages, 11 the triangulation.  Enabled by
+ * sb200_set_profiling(ctx, 1); adds an event pair around each stage. */
+SB200_API int sb200_set_profiling(sb200_ctx* ctx, int enable);
+SB200_API int sb200_get_stage_ms(sb200_ctx* ctx, double* ms16, int reset);
+/* Counters of the refinement kernel: [0] = table hits, [1] = exact on-the-fly evaluations. */
+SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
+
+/* glibc-compatible exp() used by the refinement weights (see DESIGN.md "exp"); host twin of the
+ * device function, exported so the CPU tests can pin it against the C library. */
+SB200_API double sb200_exp_host(double x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STEREO_B200_H */

@@ -1,0 +1,260 @@
+"""ctypes binding of the C ABI in include/stereo_b200.h (libstereo_b200.so).
+
+Python here is plumbing for tests and bench.py: host buffers in, host buffers out, exactly what the
+C++ mirror classes (reconstruction_b200/host) pass through the same ABI.  There is no fallback:
+if the library is missing, or no B200 is present, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libstereo_b200.so")
+CSRC = os.path.join(HERE, "csrc")
+
+NOMATCH = -10000
+STAGE_NAMES = {
+    1: "FindMargin", 2: "InitialMatch", 3: "SmoothConstraint", 4: "OrderConstraint", 5: "Uniqueness<short>#1",
+    6: "Rematch", 7: "Uniqueness<short>#2", 8: "MedianFilter", 9: "DisparityRefine", 10: "Uniqueness<double>",
+}
+
+# every symbol include/stereo_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "sb200_ctx_create", "sb200_ctx_destroy", "sb200_last_error", "sb200_status_string", "sb200_pair_upload",
+    "sb200_pair_set_calib", "sb200_match_pair", "sb200_match_one_layer", "sb200_run_stage", "sb200_set_refine_iters",
+    "sb200_disparity_info", "sb200_get_disparity", "sb200_set_disparity", "sb200_get_rematch_bounds", "sb200_get_level",
+    "sb200_get_margin", "sb200_triangulate", "sb200_get_points", "sb200_points_device", "sb200_match_pair_host",
+    "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
+    "sb200_exp_host",
+]
+
+
+class StereoError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library in tree (nvcc, sm_100a); no-op when up to date."""
+    r = subprocess.run(["make", "-s", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise StereoError("building libstereo_b200.so failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    """dlopen the library and declare the prototypes; raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise StereoError(f"{LIB_PATH} is missing - run `make -C reconstruction_b200/csrc` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    P = C.POINTER
+    protos = {
+        "sb200_ctx_create": (i32, [P(vp), i32, i32, i32, i32, i32, i32, i32, dbl, i32]),
+        "sb200_ctx_destroy": (None, [vp]),
+        "sb200_last_error": (C.c_char_p, [vp]),
+        "sb200_status_string": (C.c_char_p, [i32]),
+        "sb200_pair_upload": (i32, [vp, vp, vp, vp, vp]),
+        "sb200_pair_set_calib": (i32, [vp, vp, vp, vp]),
+        "sb200_match_pair": (i32, [vp, P(i64)]),
+        "sb200_match_one_layer": (i32, [vp, i32]),
+        "sb200_run_stage": (i32, [vp, i32, i32]),
+        "sb200_set_refine_iters": (i32, [vp, i32]),
+        "sb200_disparity_info": (i32, [vp, P(i32), P(i32), P(i32)]),
+        "sb200_get_disparity": (i32, [vp, i32, vp]),
+        "sb200_set_disparity": (i32, [vp, i32, vp, i32, i32, i32]),
+        "sb200_get_rematch_bounds": (i32, [vp, i32, vp, vp]),
+        "sb200_get_level": (i32, [vp, i32, i32, vp, vp]),
+        "sb200_get_margin": (i32, [vp, i32, i32, vp]),
+        "sb200_triangulate": (i32, [vp, P(i64)]),
+        "sb200_get_points": (i32, [vp, vp, vp, vp]),
+        "sb200_points_device": (i32, [vp, P(vp), P(vp), P(vp), P(i64)]),
+        "sb200_match_pair_host": (i32, [vp] * 11 + [i64, P(i64)]),
+        "sb200_stream": (vp, [vp]),
+        "sb200_launch_count": (i64, [vp]),
+        "sb200_set_profiling": (i32, [vp, i32]),
+        "sb200_get_stage_ms": (i32, [vp, vp, i32]),
+        "sb200_get_refine_counters": (i32, [vp, vp, i32]),
+        "sb200_exp_host": (dbl, [dbl]),
+    }
+    for name, (res, args) in protos.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _p(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor (pinned host memory in bench.py)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class StereoB200:
+    """One camera pair on one GPU; mirrors oracle.pyoracle.CpuStereo method for method."""
+
+    def __init__(self, pyrm_num, lowest_w, lowest_h, origin_w=None, origin_h=None, radius=2, ws=0.03, offset=2, device=0):
+        self.lib = load()
+        self.L = pyrm_num
+        self.lowest = (lowest_w, lowest_h)
+        self.h = C.c_void_p()
+        rc = self.lib.sb200_ctx_create(C.byref(self.h), device, pyrm_num, lowest_w, lowest_h, origin_w or 0, origin_h or 0,
+                                       radius, ws, offset)
+        if rc != 0:
+            msg = self.lib.sb200_last_error(self.h).decode() if self.h else ""
+            status = self.lib.sb200_status_string(rc).decode()
+            if self.h:
+                self.lib.sb200_ctx_destroy(self.h)
+                self.h = None
+            raise StereoError(f"sb200_ctx_create: {status} {msg}")
+
+    # ---- helpers ---------------------------------------------------------
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise StereoError(f"{what}: {self.lib.sb200_status_string(rc).decode()} - {self.lib.sb200_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def level_size(self, level):
+        return (self.lowest[0] << level, self.lowest[1] << level)
+
+    @property
+    def top_size(self):
+        return self.level_size(self.L - 1)
+
+    # ---- staging ----------------------------------------------------------
+    def set_pair(self, img0, img1, mask0, mask1):
+        self._ck(self.lib.sb200_pair_upload(self.h, _p(img0), _p(img1), _p(mask0), _p(mask1)), "pair_upload")
+
+    def set_calib(self, Q, R, T):
+        q, r, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (Q, R, T))
+        self._ck(self.lib.sb200_pair_set_calib(self.h, _p(q), _p(r), _p(t)), "pair_set_calib")
+
+    def set_refine_iters(self, n):
+        self._ck(self.lib.sb200_set_refine_iters(self.h, n), "set_refine_iters")
+
+    def get_level(self, level, view):
+        w, h = self.level_size(level)
+        img = np.empty((h, w, 3), np.uint8)
+        mask = np.empty((h, w), np.uint8)
+        self._ck(self.lib.sb200_get_level(self.h, level, view, _p(img), _p(mask)), "get_level")
+        return img, mask
+
+    def get_margins(self, level):
+        out = np.zeros((2, 6), np.int32)
+        for v in (0, 1):
+            self._ck(self.lib.sb200_get_margin(self.h, level, v, _p(out[v])), "get_margin")
+        return out
+
+    # ---- stages -------------------------------------------------------------
+    def run_stage(self, level, stage):
+        self._ck(self.lib.sb200_run_stage(self.h, level, stage), f"run_stage({level},{stage})")
+
+    def match_one_layer(self, level):
+        self._ck(self.lib.sb200_match_one_layer(self.h, level), "match_one_layer")
+
+    def match_pair(self):
+        n = C.c_int64()
+        self._ck(self.lib.sb200_match_pair(self.h, C.byref(n)), "match_pair")
+        return n.value
+
+    def disparity_info(self):
+        w, h, e = C.c_int(), C.c_int(), C.c_int()
+        self.lib.sb200_disparity_info(self.h, C.byref(w), C.byref(h), C.byref(e))
+        return w.value, h.value, e.value
+
+    def get_disparity(self, dir_):
+        w, h, e = self.disparity_info()
+        if e == 0:
+            return None
+        out = np.empty((h, w), np.int16 if e == 2 else np.float64)
+        self._ck(self.lib.sb200_get_disparity(self.h, dir_, _p(out)), "get_disparity")
+        return out
+
+    def set_disparity(self, dir_, arr):
+        a = np.ascontiguousarray(arr)
+        assert a.dtype in (np.int16, np.float64)
+        self._ck(self.lib.sb200_set_disparity(self.h, dir_, _p(a), a.shape[1], a.shape[0], a.dtype.itemsize), "set_disparity")
+
+    def get_rematch_bounds(self, dir_, level):
+        w, h = self.level_size(level)
+        bl = np.empty((h, w), np.int16)
+        br = np.empty((h, w), np.int16)
+        self._ck(self.lib.sb200_get_rematch_bounds(self.h, dir_, _p(bl), _p(br)), "get_rematch_bounds")
+        return bl, br
+
+    # ---- triangulation ----------------------------------------------------
+    def to_cloud(self):
+        n = C.c_int64()
+        self._ck(self.lib.sb200_triangulate(self.h, C.byref(n)), "triangulate")
+        return self.get_points(n.value)
+
+    def get_points(self, n):
+        xyz = np.empty((n, 3), np.float64)
+        bgr = np.empty((n, 3), np.uint8)
+        pix = np.empty(n, np.int32)
+        self._ck(self.lib.sb200_get_points(self.h, _p(xyz), _p(bgr), _p(pix)), "get_points")
+        return xyz, bgr, pix
+
+    def points_device(self):
+        x, b, p, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._ck(self.lib.sb200_points_device(self.h, C.byref(x), C.byref(b), C.byref(p), C.byref(n)), "points_device")
+        return x.value, b.value, p.value, n.value
+
+    def match_pair_host(self, img0, img1, mask0, mask1, Q, R, T, xyz_out, bgr_out, pix_out, capacity):
+        """The one-call entry the C++ mirror uses: host buffers in, points out (H2D + D2H inside)."""
+        n = C.c_int64()
+        q, r, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (Q, R, T))
+        rc = self.lib.sb200_match_pair_host(self.h, _p(img0), _p(img1), _p(mask0), _p(mask1), _p(q), _p(r), _p(t),
+                                            _p(xyz_out), _p(bgr_out), _p(pix_out), capacity, C.byref(n))
+        self._ck(rc, "match_pair_host")
+        return n.value
+
+    # ---- instrumentation ----------------------------------------------------
+    def stream(self):
+        return self.lib.sb200_stream(self.h)
+
+    def launch_count(self):
+        return int(self.lib.sb200_launch_count(self.h))
+
+    def set_profiling(self, on):
+        self._ck(self.lib.sb200_set_profiling(self.h, int(on)), "set_profiling")
+
+    def stage_ms(self, reset=True):
+        out = np.zeros(16, np.float64)
+        self._ck(self.lib.sb200_get_stage_ms(self.h, _p(out), int(reset)), "get_stage_ms")
+        return out
+
+    def refine_counters(self, reset=True):
+        out = np.zeros(2, np.int64)
+        self._ck(self.lib.sb200_get_refine_counters(self.h, _p(out), int(reset)), "get_refine_counters")
+        return out
+
+
+def exp_host(x: float) -> float:
+    return load().sb200_exp_host(float(x))

@@ -1,0 +1,611 @@
+// capi.cu — the context behind include/stereo_b200.h: device buffers for one camera pair, the fixed
+// stage order of MatchOneLayer (CStereoMatching.cpp:36-113) and the C entry points.
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <string>
+#include <vector>
+
+#include "../../include/stereo_b200.h"
+#include "kernels.h"
+
+static const unsigned long long h_exp_tab[256] = {
+#include "exp_table.inc"
+};
+extern "C" SB200_API double sb200_exp_host(double x) { return sb_exp_twin(x, h_exp_tab); }
+
+namespace {
+
+struct Level {
+  int w = 0, h = 0;
+  uint8_t* img[2] = {nullptr, nullptr};
+  uint8_t* mask[2] = {nullptr, nullptr};
+  long img_bytes = 0, mask_bytes = 0;
+  Bound margin[2];
+};
+
+}  // namespace
+
+struct sb200_ctx {
+  int device = 0, L = 0, W0 = 0, H0 = 0, OW = 0, OH = 0, R = 2, offset = 2, refine_override = -1;
+  double ws = 0.5;
+  cudaStream_t st = nullptr;
+  std::vector<Level> lv;
+  int* d_margins = nullptr;  // [L][2][4]
+  bool uploaded = false, calib_set = false;
+  // disparity state (cv::Mat disparity[2] of MatchAllLayer)
+  short* ds[2] = {nullptr, nullptr};
+  short* ds_tmp = nullptr;
+  short *range_lo = nullptr, *range_hi = nullptr;
+  short *BL[2] = {nullptr, nullptr}, *BR[2] = {nullptr, nullptr};
+  double* f64buf[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* dd[2] = {nullptr, nullptr};
+  int dw = 0, dh = 0, elem = 0;
+  // per-level window statistics
+  double2* stats[2] = {nullptr, nullptr};
+  int stats_level = -1;
+  // refinement
+  RefineScratch rs{};
+  // triangulation
+  CloudScratch cs{};
+  short* d_ellipse = nullptr;
+  int erode_ks = 0;
+  double Q[16], Rf[9], Tf[3];
+  double* xyz = nullptr;
+  uint8_t* bgr = nullptr;
+  int* pix = nullptr;
+  int* d_npoints = nullptr;
+  int* h_npoints = nullptr;  // pinned
+  int64_t n_points = 0;
+  // instrumentation
+  int64_t launches = 0;
+  bool profiling = false;
+  struct Ev { int stage; cudaEvent_t a, b; };
+  std::vector<Ev> events;
+  double stage_ms[16] = {0};
+  std::string err;
+  Bound cur_margin[2];
+  int cur_level = -1;
+};
+
+namespace {
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess) {                                                              \
+      char b_[512];                                                                       \
+      snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+      c->err = b_;                                                                        \
+      return SB200_ERR_CUDA;                                                              \
+    }                                                                                     \
+  } while (0)
+
+template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+struct StageTimer {
+  sb200_ctx* c;
+  sb200_ctx::Ev ev{};
+  bool on;
+  StageTimer(sb200_ctx* c_, int stage) : c(c_), on(c_->profiling) {
+    if (!on) return;
+    ev.stage = stage;
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, c->st);
+  }
+  ~StageTimer() {
+    if (!on) return;
+    cudaEventRecord(ev.b, c->st);
+    c->events.push_back(ev);
+  }
+};
+
+PairViews make_views(const sb200_ctx* c, int level, bool zeroOne) {
+  const Level& l = c->lv[level];
+  PairViews v;
+  const int s = zeroOne ? 0 : 1, t = zeroOne ? 1 : 0;
+  v.img0 = l.img[s]; v.img1 = l.img[t];
+  v.mask0 = l.mask[s]; v.mask1 = l.mask[t];
+  v.stat0 = c->stats[s]; v.stat1 = c->stats[t];
+  v.W = l.w; v.H = l.h;
+  v.img_bytes = l.img_bytes; v.mask_bytes = l.mask_bytes;
+  return v;
+}
+
+int ensure_stats(sb200_ctx* c, int level) {
+  if (c->stats_level == level) return SB200_OK;
+  const Level& l = c->lv[level];
+  for (int k = 0; k < 2; k++) {
+    const int n = launch_window_stats(l.img[k], l.w, l.h, c->R, c->stats[k], c->st);
+    if (n < 0) { c->err = "unsupported MatchBlockRadius (1..3)"; return SB200_ERR_BAD_ARG; }
+    c->launches += n;
+  }
+  c->stats_level = level;
+  return SB200_OK;
+}
+
+bool degenerate(const Bound& m) { return m.YL >= m.YR || m.XL >= m.XR; }
+
+int run_stage_impl(sb200_ctx* c, int level, int stage) {
+  if (!c->uploaded) { c->err = "no pair uploaded"; return SB200_ERR_STATE; }
+  if (level < 0 || level >= c->L) { c->err = "level out of range"; return SB200_ERR_BAD_ARG; }
+  const Level& l = c->lv[level];
+  const int W = l.w, H = l.h;
+  StageTimer timer(c, stage);
+  if (stage == SB200_STAGE_FIND_MARGIN) {  // margins were reduced on the device at upload
+    c->cur_margin[0] = l.margin[0];
+    c->cur_margin[1] = l.margin[1];
+    c->cur_level = level;
+    return SB200_OK;
+  }
+  if (c->cur_level != level) { c->err = "run FindMargin (stage 1) of this level first"; return SB200_ERR_STATE; }
+  const Bound m0 = c->cur_margin[0], m1 = c->cur_margin[1];
+  // direction d: source margin = margin[d], target margin = margin[1-d]  (margin[!IsZeroOne], margin[IsZeroOne])
+  const Bound msrc[2] = {m0, m1}, mtgt[2] = {m1, m0};
+  switch (stage) {
+    case SB200_STAGE_INITIAL_MATCH: {
+      int rc = ensure_stats(c, level);
+      if (rc) return rc;
+      if (level == 0) {
+        for (int d = 0; d < 2; d++) {
+          const int n = launch_lowest_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->ds[d], c->st);
+          if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
+        }
+      } else {
+        if (c->elem != 8 || c->dw != c->lv[level - 1].w || c->dh != c->lv[level - 1].h) {
+          c->err = "HighLevelInitialMatch needs the refined f64 maps of the previous level";
+          return SB200_ERR_STATE;
+        }
+        for (int d = 0; d < 2; d++) {
+          const int n = launch_high_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->offset, c->dd[d], c->dw,
+                                          c->dh, c->range_lo, c->range_hi, c->ds[d], c->st);
+          if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
+        }
+      }
+      c->dw = W; c->dh = H; c->elem = 2;
+      break;
+    }
+    case SB200_STAGE_SMOOTH:
+    case SB200_STAGE_ORDER:
+    case SB200_STAGE_UNIQUE_1:
+    case SB200_STAGE_REMATCH:
+    case SB200_STAGE_UNIQUE_2:
+    case SB200_STAGE_MEDIAN:
+    case SB200_STAGE_REFINE: {
+      if (c->elem != 2 || c->dw != W || c->dh != H) { c->err = "stage needs s16 disparity maps of this level"; return SB200_ERR_STATE; }
+      if (stage == SB200_STAGE_SMOOTH) {
+        for (int d = 0; d < 2; d++) {
+          c->launches += launch_smooth(c->ds[d], c->ds_tmp, W, H, msrc[d], c->st);
+          std::swap(c->ds[d], c->ds_tmp);
+        }
+      } else if (stage == SB200_STAGE_ORDER) {
+        for (int d = 0; d < 2; d++) c->launches += launch_order(c->ds[d], W, H, msrc[d], c->st);
+      } else if (stage == SB200_STAGE_UNIQUE_1 || stage == SB200_STAGE_UNIQUE_2) {  // :456-460
+        c->launches += launch_unique_s16(c->ds[0], c->ds[1], W, H, msrc[0], mtgt[0], c->st);
+        c->launches += launch_unique_s16(c->ds[1], c->ds[0], W, H, msrc[1], mtgt[1], c->st);
+        c->launches += launch_unique_s16(c->ds[0], c->ds[1], W, H, msrc[0], mtgt[0], c->st);
+      } else if (stage == SB200_STAGE_REMATCH) {
+        int rc = ensure_stats(c, level);
+        if (rc) return rc;
+        for (int d = 0; d < 2; d++) {
+          if (degenerate(msrc[d])) { c->err = "degenerate margin in SetBoundary_smooth (reference exits)"; return SB200_ERR_DEGENERATE_MARGIN; }
+          const PairViews v = make_views(c, level, d == 0);
+          c->launches += launch_rematch_bounds(c->ds[d], v.mask0, W, H, msrc[d], mtgt[d], c->BL[d], c->BR[d], c->st);
+          const int n = launch_rematch_search(v, msrc[d], c->R, c->BL[d], c->BR[d], c->ds[d], c->st);
+          if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
+        }
+      } else if (stage == SB200_STAGE_MEDIAN) {
+        for (int d = 0; d < 2; d++) {
+          c->launches += launch_median(c->ds[d], l.mask[d], c->ds_tmp, W, H, msrc[d], c->st);
+          std::swap(c->ds[d], c->ds_tmp);
+        }
+      } else {  // refine
+        const int it = c->refine_override >= 0 ? c->refine_override : 30 + level * 30;  // :95
+        for (int d = 0; d < 2; d++) {
+          RefineScratch s = c->rs;
+          s.A = c->f64buf[2 * d];
+          s.B = c->f64buf[2 * d + 1];
+          double* res = nullptr;
+          c->launches += launch_refine(make_views(c, level, d == 0), msrc[d], c->ds[d], it, c->ws, s, &res, c->st);
+          c->dd[d] = res;
+        }
+        c->elem = 8;
+      }
+      break;
+    }
+    case SB200_STAGE_UNIQUE_3: {
+      if (c->elem != 8 || c->dw != W || c->dh != H) { c->err = "stage needs f64 disparity maps of this level"; return SB200_ERR_STATE; }
+      c->launches += launch_unique_f64(c->dd[0], c->dd[1], W, H, msrc[0], mtgt[0], c->st);
+      c->launches += launch_unique_f64(c->dd[1], c->dd[0], W, H, msrc[1], mtgt[1], c->st);
+      c->launches += launch_unique_f64(c->dd[0], c->dd[1], W, H, msrc[0], mtgt[0], c->st);
+      break;
+    }
+    default:
+      c->err = "unknown stage";
+      return SB200_ERR_BAD_ARG;
+  }
+  CK(cudaGetLastError());
+  return SB200_OK;
+}
+
+int triangulate_impl(sb200_ctx* c, bool sync) {
+  if (!c->calib_set) { c->err = "calibration not set"; return SB200_ERR_STATE; }
+  const int level = c->L - 1;
+  const Level& l = c->lv[level];
+  if (c->elem != 8 || c->dw != l.w || c->dh != l.h) { c->err = "triangulation needs the refined top-level map"; return SB200_ERR_STATE; }
+  StageTimer timer(c, 11);
+  const double scale = double(c->W0) / c->OW * (1 << level);  // :692
+  CloudParams p;
+  p.q03 = c->Q[3] * scale; p.q13 = c->Q[7] * scale; p.q23 = c->Q[11] * scale; p.q33 = c->Q[15] * scale;  // :697-698
+  p.q32 = c->Q[14];
+  memcpy(p.R, c->Rf, sizeof p.R);
+  memcpy(p.T, c->Tf, sizeof p.T);
+  c->launches += launch_cloud(c->dd[0], l.mask[0], l.img[0], l.w, l.h, l.margin[0], c->erode_ks, p, c->cs, c->xyz, c->bgr,
+                              c->pix, c->d_npoints, c->st);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(c->h_npoints, c->d_npoints, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  if (sync) {
+    CK(cudaStreamSynchronize(c->st));
+    c->n_points = *c->h_npoints;
+  }
+  return SB200_OK;
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+const char* sb200_status_string(int s) {
+  switch (s) {
+    case SB200_OK: return "ok";
+    case SB200_ERR_NO_DEVICE: return "no CUDA device (this library has no CPU path)";
+    case SB200_ERR_BAD_ARG: return "bad argument";
+    case SB200_ERR_CUDA: return "CUDA error";
+    case SB200_ERR_STATE: return "call order violated";
+    case SB200_ERR_DEGENERATE_MARGIN: return "degenerate mask margin";
+  }
+  return "unknown status";
+}
+
+const char* sb200_last_error(const sb200_ctx* c) { return c ? c->err.c_str() : ""; }
+
+int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, int lowest_h, int origin_w, int origin_h,
+                     int radius, double ws, int offset) {
+  if (!out) return SB200_ERR_BAD_ARG;
+  *out = nullptr;
+  if (pyrm_num < 1 || pyrm_num > SB_MAX_LEVELS || lowest_w < 8 || lowest_h < 8 || radius < 1 || radius > 2) return SB200_ERR_BAD_ARG;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SB200_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return SB200_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return SB200_ERR_NO_DEVICE;
+  sb200_ctx* c = new sb200_ctx();
+  c->device = device; c->L = pyrm_num; c->W0 = lowest_w; c->H0 = lowest_h;
+  c->OW = origin_w > 0 ? origin_w : lowest_w << (pyrm_num - 1);
+  c->OH = origin_h > 0 ? origin_h : lowest_h << (pyrm_num - 1);
+  c->R = radius; c->ws = ws; c->offset = offset;
+  *out = c;  // returned even on failure so the caller can read sb200_last_error, then destroy
+  CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  c->lv.resize(pyrm_num);
+  for (int i = 0; i < pyrm_num; i++) {
+    Level& l = c->lv[i];
+    l.w = lowest_w << i; l.h = lowest_h << i;
+    l.img_bytes = (long)l.w * l.h * 3 + SB_IMG_SLACK;
+    l.mask_bytes = (long)l.w * l.h + SB_IMG_SLACK;
+    for (int k = 0; k < 2; k++) {
+      CK(dalloc(&l.img[k], l.img_bytes));
+      CK(dalloc(&l.mask[k], l.mask_bytes));
+      CK(cudaMemsetAsync(l.img[k], 0, l.img_bytes, c->st));
+      CK(cudaMemsetAsync(l.mask[k], 0, l.mask_bytes, c->st));
+    }
+  }
+  const size_t n = (size_t)c->lv[pyrm_num - 1].w * c->lv[pyrm_num - 1].h;
+  const size_t pad = 256;
+  CK(dalloc(&c->d_margins, pyrm_num * 8));
+  for (int d = 0; d < 2; d++) {
+    CK(dalloc(&c->ds[d], n + pad));
+    CK(dalloc(&c->BL[d], n + pad));
+    CK(dalloc(&c->BR[d], n + pad));
+    CK(dalloc(&c->stats[d], n + pad));
+  }
+  CK(dalloc(&c->ds_tmp, n + pad));
+  CK(dalloc(&c->range_lo, n + pad));
+  CK(dalloc(&c->range_hi, n + pad));
+  for (int k = 0; k < 4; k++) CK(dalloc(&c->f64buf[k], n + pad));
+  CK(dalloc(&c->rs.table, (size_t)SB_REFINE_K * n + pad));
+  CK(dalloc(&c->rs.code, n + pad));
+  CK(dalloc(&c->rs.counters, 2));
+  CK(cudaMemsetAsync(c->rs.counters, 0, 2 * sizeof(unsigned long long), c->st));
+  CK(dalloc(&c->cs.run, n + pad));
+  CK(dalloc(&c->cs.eroded, n + pad));
+  CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));
+  CK(dalloc(&c->cs.row_offset, (size_t)c->lv[pyrm_num - 1].h + 2));
+  c->erode_ks = (int)ceil(0.02 * c->lv[pyrm_num - 1].h);  // :703
+  {
+    std::vector<short> j12(2 * (size_t)c->erode_ks);
+    sb_ellipse_rows(c->erode_ks, j12.data(), j12.data() + c->erode_ks);
+    CK(dalloc(&c->d_ellipse, j12.size()));
+    CK(cudaMemcpy(c->d_ellipse, j12.data(), j12.size() * sizeof(short), cudaMemcpyHostToDevice));
+    c->cs.ellipse = c->d_ellipse;
+  }
+  CK(dalloc(&c->xyz, 3 * n));
+  CK(dalloc(&c->bgr, 3 * n));
+  CK(dalloc(&c->pix, n));
+  CK(dalloc(&c->d_npoints, 1));
+  CK(cudaMallocHost((void**)&c->h_npoints, sizeof(int)));
+  *c->h_npoints = 0;
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+void sb200_ctx_destroy(sb200_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->st) cudaStreamSynchronize(c->st);
+  for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  for (auto& l : c->lv)
+    for (int k = 0; k < 2; k++) { cudaFree(l.img[k]); cudaFree(l.mask[k]); }
+  cudaFree(c->d_margins);
+  for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); }
+  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi);
+  for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
+  cudaFree(c->rs.table); cudaFree(c->rs.code); cudaFree(c->rs.counters);
+  cudaFree(c->cs.run); cudaFree(c->cs.eroded); cudaFree(c->cs.row_count); cudaFree(c->cs.row_offset);
+  cudaFree(c->d_ellipse);
+  cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
+  if (c->h_npoints) cudaFreeHost(c->h_npoints);
+  if (c->st) cudaStreamDestroy(c->st);
+  delete c;
+}
+
+int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1) {
+  if (!c || !bgr0 || !bgr1 || !mask0 || !mask1) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  StageTimer timer(c, 0);
+  Level& top = c->lv[c->L - 1];
+  const size_t npx = (size_t)top.w * top.h;
+  const uint8_t* im[2] = {bgr0, bgr1};
+  const uint8_t* mk[2] = {mask0, mask1};
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMemcpyAsync(top.img[k], im[k], npx * 3, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(top.mask[k], mk[k], npx, cudaMemcpyHostToDevice, c->st));
+  }
+  for (int k = 0; k < 2; k++)  // ConstructPyrm :1040-1053
+    for (int i = c->L - 1; i > 0; i--) {
+      c->launches += launch_pyrdown(c->lv[i].img[k], c->lv[i].w, c->lv[i].h, 3, c->lv[i - 1].img[k], c->st);
+      c->launches += launch_pyrdown(c->lv[i].mask[k], c->lv[i].w, c->lv[i].h, 1, c->lv[i - 1].mask[k], c->st);
+    }
+  for (int i = 0; i < c->L; i++)
+    for (int k = 0; k < 2; k++)
+      c->launches += launch_find_margin(c->lv[i].mask[k], c->lv[i].w, c->lv[i].h, c->R, c->d_margins + (i * 2 + k) * 4, c->st);
+  CK(cudaGetLastError());
+  std::vector<int> hm((size_t)c->L * 8);
+  CK(cudaMemcpyAsync(hm.data(), c->d_margins, hm.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  for (int i = 0; i < c->L; i++)
+    for (int k = 0; k < 2; k++) {
+      const int* m = &hm[(size_t)(i * 2 + k) * 4];
+      Bound& b = c->lv[i].margin[k];
+      b.YL = m[0]; b.YR = m[1]; b.XL = m[2]; b.XR = m[3];
+      b.width = b.XR - b.XL + 1;   // :1036-1037
+      b.height = b.YR - b.YL + 1;
+    }
+  c->uploaded = true;
+  c->elem = 0; c->dw = c->dh = 0;
+  c->stats_level = -1;
+  c->cur_level = -1;
+  return SB200_OK;
+}
+
+int sb200_pair_set_calib(sb200_ctx* c, const double* Q, const double* R_final, const double* T_final) {
+  if (!c || !Q || !R_final || !T_final) return SB200_ERR_BAD_ARG;
+  memcpy(c->Q, Q, sizeof c->Q);
+  memcpy(c->Rf, R_final, sizeof c->Rf);
+  memcpy(c->Tf, T_final, sizeof c->Tf);
+  c->calib_set = true;
+  return SB200_OK;
+}
+
+int sb200_run_stage(sb200_ctx* c, int level, int stage) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = run_stage_impl(c, level, stage);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_match_one_layer(sb200_ctx* c, int level) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  for (int s = 1; s <= 10; s++) {
+    int rc = run_stage_impl(c, level, s);
+    if (rc) return rc;
+  }
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+static int match_pair_async(sb200_ctx* c) {
+  for (int i = 0; i < c->L; i++)
+    for (int s = 1; s <= 10; s++) {
+      int rc = run_stage_impl(c, i, s);
+      if (rc) return rc;
+    }
+  return triangulate_impl(c, false);
+}
+
+int sb200_match_pair(sb200_ctx* c, int64_t* n_points) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = match_pair_async(c);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(c->st));
+  c->n_points = *c->h_npoints;
+  if (n_points) *n_points = c->n_points;
+  return SB200_OK;
+}
+
+int sb200_set_refine_iters(sb200_ctx* c, int n) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  c->refine_override = n;
+  return SB200_OK;
+}
+
+int sb200_disparity_info(const sb200_ctx* c, int* w, int* h, int* es) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  if (w) *w = c->dw;
+  if (h) *h = c->dh;
+  if (es) *es = c->elem;
+  return SB200_OK;
+}
+
+int sb200_get_disparity(sb200_ctx* c, int dir, void* host_out) {
+  if (!c || dir < 0 || dir > 1 || !host_out) return SB200_ERR_BAD_ARG;
+  if (c->elem == 0) { c->err = "no disparity yet"; return SB200_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->dw * c->dh;
+  const void* src = c->elem == 2 ? (const void*)c->ds[dir] : (const void*)c->dd[dir];
+  CK(cudaMemcpyAsync(host_out, src, n * c->elem, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_set_disparity(sb200_ctx* c, int dir, const void* host_in, int width, int height, int es) {
+  if (!c || dir < 0 || dir > 1 || !host_in || (es != 2 && es != 8)) return SB200_ERR_BAD_ARG;
+  const Level& top = c->lv[c->L - 1];
+  if (width <= 0 || height <= 0 || (size_t)width * height > (size_t)top.w * top.h) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)width * height;
+  if (es == 2) {
+    CK(cudaMemcpyAsync(c->ds[dir], host_in, n * 2, cudaMemcpyHostToDevice, c->st));
+  } else {
+    c->dd[dir] = c->f64buf[2 * dir];
+    CK(cudaMemcpyAsync(c->dd[dir], host_in, n * 8, cudaMemcpyHostToDevice, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  c->dw = width; c->dh = height; c->elem = es;
+  return SB200_OK;
+}
+
+int sb200_get_rematch_bounds(sb200_ctx* c, int dir, int16_t* bl, int16_t* br) {
+  if (!c || dir < 0 || dir > 1 || !bl || !br) return SB200_ERR_BAD_ARG;
+  if (c->cur_level < 0) { c->err = "no level processed"; return SB200_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  const Level& l = c->lv[c->cur_level];
+  const size_t n = (size_t)l.w * l.h;
+  CK(cudaMemcpyAsync(bl, c->BL[dir], n * 2, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(br, c->BR[dir], n * 2, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_get_level(sb200_ctx* c, int level, int view, uint8_t* bgr_out, uint8_t* mask_out) {
+  if (!c || level < 0 || level >= c->L || view < 0 || view > 1) return SB200_ERR_BAD_ARG;
+  if (!c->uploaded) { c->err = "no pair uploaded"; return SB200_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  const Level& l = c->lv[level];
+  const size_t n = (size_t)l.w * l.h;
+  if (bgr_out) CK(cudaMemcpyAsync(bgr_out, l.img[view], n * 3, cudaMemcpyDeviceToHost, c->st));
+  if (mask_out) CK(cudaMemcpyAsync(mask_out, l.mask[view], n, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_get_margin(const sb200_ctx* c, int level, int view, sb200_boundary* out) {
+  if (!c || level < 0 || level >= c->L || view < 0 || view > 1 || !out) return SB200_ERR_BAD_ARG;
+  if (!c->uploaded) return SB200_ERR_STATE;
+  const Bound& b = c->lv[level].margin[view];
+  out->YL = b.YL; out->YR = b.YR; out->XL = b.XL; out->XR = b.XR; out->width = b.width; out->height = b.height;
+  return SB200_OK;
+}
+
+int sb200_triangulate(sb200_ctx* c, int64_t* n_points) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = triangulate_impl(c, true);
+  if (rc) return rc;
+  if (n_points) *n_points = c->n_points;
+  return SB200_OK;
+}
+
+int sb200_get_points(sb200_ctx* c, double* xyz_out, uint8_t* bgr_out, int32_t* pix_out) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)c->n_points;
+  if (n) {
+    if (xyz_out) CK(cudaMemcpyAsync(xyz_out, c->xyz, n * 24, cudaMemcpyDeviceToHost, c->st));
+    if (bgr_out) CK(cudaMemcpyAsync(bgr_out, c->bgr, n * 3, cudaMemcpyDeviceToHost, c->st));
+    if (pix_out) CK(cudaMemcpyAsync(pix_out, c->pix, n * 4, cudaMemcpyDeviceToHost, c->st));
+  }
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_points_device(sb200_ctx* c, void** xyz_dev, void** bgr_dev, void** pix_dev, int64_t* n_points) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  if (xyz_dev) *xyz_dev = c->xyz;
+  if (bgr_dev) *bgr_dev = c->bgr;
+  if (pix_dev) *pix_dev = c->pix;
+  if (n_points) *n_points = c->n_points;
+  return SB200_OK;
+}
+
+int sb200_match_pair_host(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1,
+                          const double* Q, const double* R_final, const double* T_final, double* xyz_out, uint8_t* bgr_out,
+                          int32_t* pix_out, int64_t capacity, int64_t* n_points) {
+  int rc = sb200_pair_upload(c, bgr0, bgr1, mask0, mask1);
+  if (rc) return rc;
+  rc = sb200_pair_set_calib(c, Q, R_final, T_final);
+  if (rc) return rc;
+  int64_t n = 0;
+  rc = sb200_match_pair(c, &n);
+  if (rc) return rc;
+  if (n_points) *n_points = n;
+  if (n > capacity) { c->err = "point buffers too small"; return SB200_ERR_BAD_ARG; }
+  return sb200_get_points(c, xyz_out, bgr_out, pix_out);
+}
+
+void* sb200_stream(sb200_ctx* c) { return c ? (void*)c->st : nullptr; }
+int64_t sb200_launch_count(const sb200_ctx* c) { return c ? c->launches : 0; }
+
+int sb200_set_profiling(sb200_ctx* c, int enable) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  c->profiling = enable != 0;
+  return SB200_OK;
+}
+
+int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
+  if (!c || !ms16) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->st));
+  for (auto& e : c->events) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 16) c->stage_ms[e.stage] += ms;
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  c->events.clear();
+  memcpy(ms16, c->stage_ms, sizeof c->stage_ms);
+  if (reset) memset(c->stage_ms, 0, sizeof c->stage_ms);
+  return SB200_OK;
+}
+
+int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
+  if (!c || !out2) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->st));
+  unsigned long long h[2];
+  CK(cudaMemcpy(h, c->rs.counters, sizeof h, cudaMemcpyDeviceToHost));
+  out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
+  if (reset) CK(cudaMemset(c->rs.counters, 0, sizeof h));
+  return SB200_OK;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

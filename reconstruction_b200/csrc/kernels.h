@@ -1,0 +1,74 @@
+// kernels.h — host-callable launchers of the sm_100a kernels (one per reference sweep).
+// Every launcher enqueues on `st` and returns the number of kernel launches it issued.
+#pragma once
+#include "common.cuh"
+
+struct PairViews {  // source / target view of one matching direction (image / image_inv, :43-50)
+  const uint8_t *img0, *img1, *mask0, *mask1;
+  const double2 *stat0, *stat1;  // per-pixel (mean, norm) of the 5x5x3 window (WindowToVec)
+  int W, H;
+  long img_bytes;   // readable bytes of an image buffer (payload + slack)
+  long mask_bytes;  // readable bytes of a mask buffer
+};
+
+// K0  ConstructPyrm (CStereoMatching.cpp:1040-1053): pyrDown of an interleaved u8 image, cn = 1 or 3.
+int launch_pyrdown(const uint8_t* src, int W, int H, int cn, uint8_t* dst, cudaStream_t st);
+// K1  FindMargin (:1011-1038): out[4] = {YL, YR, XL, XR} (device ints, initialised by the kernel).
+int launch_find_margin(const uint8_t* mask, int W, int H, int R, int* out4, cudaStream_t st);
+// per-pixel WindowToVec statistics of the (2R+1)^2*3 window centred on each pixel (CManageData.cpp:81-90)
+int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats, cudaStream_t st);
+
+// K2  LowestLevelInitialMatch (:170-227)
+int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st);
+// K3  HighLevelInitialMatch (:231-308): prev = refined f64 map of the coarser level (pw x ph)
+int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
+                      short* lo_scratch, short* hi_scratch, short* out, cudaStream_t st);
+// K4  SmoothConstraint (:370-448): in -> out (out-of-place gather formulation)
+int launch_smooth(const short* in, short* out, int W, int H, Bound m, cudaStream_t st);
+// K5  OrderConstraint (:310-368): in place
+int launch_order(short* disp, int W, int H, Bound m, cudaStream_t st);
+// K6  one pass of UniquenessContraint_ (:462-497): P is filtered against Qm, in place
+int launch_unique_s16(short* P, const short* Qm, int W, int H, Bound ms, Bound mt, cudaStream_t st);
+int launch_unique_f64(double* P, const double* Qm, int W, int H, Bound ms, Bound mt, cudaStream_t st);
+// K7  SetBoundary_smooth (:817-942) then the NCC search of Rematch (:499-570)
+int launch_rematch_bounds(const short* disp, const uint8_t* mask, int W, int H, Bound ms, Bound mt, short* BL, short* BR,
+                          cudaStream_t st);
+int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp,
+                          cudaStream_t st);
+// K8  MedianFilter (:763-815), one iteration
+int launch_median(const short* in, const uint8_t* mask, short* out, int W, int H, Bound m, cudaStream_t st);
+
+// K9  DisparityRefine (:572-680)
+struct RefineScratch {
+  double* A;           // W*H  ping
+  double* B;           // W*H  pong
+  double2* table;      // K_REFINE * W*H entries (pwp, c)
+  unsigned short* code;  // W*H  packed (table base, mode)
+  unsigned long long* counters;  // [2]
+};
+#define SB_REFINE_K 4      // table entries per pixel: im - im0 in [-2, 1]
+#define SB_REFINE_KLO (-2)
+// Returns launches; *result receives the buffer (A or B) that holds the refined map.
+int launch_refine(const PairViews& v, Bound ms, const short* in, int iterations, double ws, const RefineScratch& s,
+                  double** result, cudaStream_t st);
+
+// K10 DisparityToCloud<double> (:682-761)
+struct CloudScratch {
+  unsigned short* run;   // W*H  horizontal run length of mask == 255
+  uint8_t* eroded;       // W*H  1 where the eroded mask is 255
+  int* row_count;        // H + 1
+  int* row_offset;       // H + 1
+  const short* ellipse;  // [2*ks]: j1[ks] then j2[ks], row extents of the MORPH_ELLIPSE element
+};
+// getStructuringElement(MORPH_ELLIPSE, ks x ks) row extents [j1, j2) (host)
+void sb_ellipse_rows(int ks, short* j1, short* j2);
+struct CloudParams {
+  double q03, q13, q23, q32, q33;  // Q with column 3 already scaled (:697-698)
+  double R[9], T[3];
+};
+int launch_cloud(const double* disp, const uint8_t* mask, const uint8_t* img, int W, int H, Bound m, int erode_ks,
+                 const CloudParams& p, const CloudScratch& s, double* xyz, uint8_t* bgr, int* pix, int* n_points_dev,
+                 cudaStream_t st);
+
+// s16 -> f64 conversion (Mat::convertTo, :585,587) and fills
+int launch_fill_s16(short* p, long n, short v, cudaStream_t st);

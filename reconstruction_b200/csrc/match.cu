@@ -1,0 +1,205 @@
+// match.cu — K2 LowestLevelInitialMatch, K3 HighLevelInitialMatch, and the NCC search of K7 Rematch.
+//
+// All three are the same loop in the reference (CStereoMatching.cpp:202-218, :268-300, :535-562):
+// for a masked source pixel, argmax over target columns im in [lo, hi] with mask1 == 255 of
+//     dot(vecL / normL, vecR) / normR          (strict '>' from -1, first maximum wins)
+// and differ only in where [lo, hi] comes from.  One kernel (k_ncc_search) serves them:
+//   * G lanes share one source pixel: they build vecL/normL once into shared memory (element-wise
+//     work, order-free), then each lane evaluates candidates lo+lane, lo+lane+G, ... in the
+//     reference's summation order and the group merges (value, index) with shuffles;
+//   * (mean, norm) of every target window come from the per-level statistics map, so a candidate
+//     costs one 75-term dot product;
+//   * a block owns a 256-pixel scanline segment, compacts its active pixels in shared memory and
+//     deals them to its groups, so lanes are not parked on unmasked / already matched pixels.
+// Target windows are addressed flat (y*W + im), as the reference's pointer arithmetic does, so a
+// range that overruns the row (Rematch quirk at x == XL, :938-939) lands on the same bytes.
+#include "kernels.h"
+#include "ncc_exact.cuh"
+
+enum { SEARCH_LOWEST = 0, SEARCH_RANGE_MAPS = 1, SEARCH_REMATCH = 2 };
+
+template <int WS, int G, int MODE>
+__global__ void __launch_bounds__(256) k_ncc_search(PairViews v, Bound ms, int lo_const, int hi_const,
+                                                    const short* __restrict__ lo_map, const short* __restrict__ hi_map,
+                                                    short* __restrict__ disp) {
+  constexpr int R = WS / 2, N = WS * WS * 3, NG = 256 / G;
+  __shared__ double s_vec[NG][N];
+  __shared__ short s_list[256];
+  __shared__ int s_n;
+
+  const int y = ms.YL + blockIdx.y;
+  const int x0 = ms.XL + blockIdx.x * 256;
+  const int W = v.W, pitch = 3 * W;
+  const long n_px = (long)W * v.H;
+  const long stat_first = (long)R * W + R, stat_last = n_px - stat_first;
+
+  // ---- compact the active pixels of this segment (ascending x) --------------------------------
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  {
+    const int x = x0 + threadIdx.x;
+    bool act = false;
+    if (x <= ms.XR) {
+      act = v.mask0[(size_t)y * W + x] == 255;
+      if (MODE == SEARCH_REMATCH) act = act && disp[(size_t)y * W + x] == SB_NOMATCH;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && bal) base = atomicAdd(&s_n, __popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (act) s_list[base + __popc(bal & ((1u << (threadIdx.x & 31)) - 1))] = (short)threadIdx.x;
+  }
+  __syncthreads();
+  const int n_act = s_n;
+  const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1) << ((threadIdx.x & 31) / G * G));
+  double* vec = s_vec[gid];
+
+  for (int a = gid; a < n_act; a += NG) {
+    const int x = x0 + s_list[a];
+    const long f = (long)y * W + x;
+    // ---- vecL = (window - mean) / normL --------------------------------------------------------
+    const double2 sl = v.stat0[f];
+    const double yl = 1.0 / sl.y;
+    const uint8_t* pl = v.img0 + 3 * (f - stat_first);
+    for (int k = gl; k < N; k += G) {
+      const int j = k / WS, i = k - j * WS;
+      vec[k] = div_by_common((double)pl[i * pitch + j] - sl.x, sl.y, yl);
+    }
+    __syncwarp(gmask);
+    // ---- candidate range ----------------------------------------------------------------------
+    int lo, hi;
+    if (MODE == SEARCH_LOWEST) { lo = lo_const; hi = hi_const; }
+    else { lo = lo_map[f]; hi = hi_map[f]; }
+    double bv = -1.0;
+    int bi = -1;
+    for (int im = lo + gl; im <= hi; im += G) {
+      const long ft = (long)y * W + im;
+      if (ft < 0 || ft >= v.mask_bytes) continue;
+      if (v.mask1[ft] != 255) continue;
+      double val;
+      if (ft >= stat_first && ft < stat_last) {
+        const double2 sr = v.stat1[ft];
+        val = window_dot_exact<WS>(vec, 1, v.img1 + 3 * (ft - stat_first), pitch, sr.x) / sr.y;
+      } else {  // window leaves the payload: bounds-checked evaluation
+        double mr;
+        const long off0 = 3 * (ft - stat_first);
+        const double nr = window_stats_checked<WS>(v.img1, off0, v.img_bytes, pitch, mr);
+        val = window_dot_checked<WS>(vec, 1, v.img1, off0, v.img_bytes, pitch, mr) / nr;
+      }
+      if (val > bv) { bv = val; bi = im; }
+    }
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(gmask, bv, o, G);
+      const int oi = __shfl_xor_sync(gmask, bi, o, G);
+      if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (gl == 0 && bi >= 0) disp[f] = (short)((unsigned short)bi - x);  // ushort temp_i; short(temp_i - x) (:271,:302)
+    __syncwarp(gmask);
+  }
+}
+
+template <int G, int MODE>
+static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, const short* lo_map, const short* hi_map,
+                           short* disp, cudaStream_t st) {
+  if (ms.width <= 0 || ms.height <= 0) return 0;
+  dim3 grid((ms.width + 255) / 256, ms.height);
+  if (R == 2) k_ncc_search<5, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
+  else if (R == 1) k_ncc_search<3, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
+  else return -1;
+  return 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2  LowestLevelInitialMatch (:170-227): full-range search over [XL1, XR1], one warp per pixel.
+// ------------------------------------------------------------------------------------------------
+int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st) {
+  int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
+  n += search_dispatch<32, SEARCH_LOWEST>(v, ms, R, mt.XL, mt.XR, nullptr, nullptr, out, st);
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3 ranges (:259-288).  Sequential-in-row state of the reference (quirk Q3): boundary_L/R start at
+// [XL1, XR1] per row and are only updated at masked pixels:
+//   coarse sample s valid : L = max(x + int(2s+.5) - off, XL1), R = min(x + int(2s+.5) + off, XR1)
+//   coarse sample NOMATCH : L carried; R = min(i + int(2 s[i]) + off + 1, XR1) for the first valid
+//                           coarse index i > t2 (coarse index, as written), else carried.
+// Both are last-writer scans; one warp walks a row in 32-pixel chunks with ballot + shuffle.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_high_ranges(const uint8_t* __restrict__ mask0, int W, Bound ms, Bound mt, int off,
+                                                     const double* __restrict__ prev, int pw,
+                                                     short* __restrict__ lo_map, short* __restrict__ hi_map) {
+  extern __shared__ short s_next[];  // [warps][pw]: first valid coarse index > i, or -1
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = ms.YL + blockIdx.x * (blockDim.x >> 5) + warp;
+  if (y > ms.YR) return;
+  short* nv = s_next + warp * pw;
+  const double* s = prev + (size_t)((y + 1) >> 1) * pw;  // int((y+1)/2.0), y >= 0
+  const int imax = ms.XR >> 1;                           // look-ahead stops at XR>>1 (:275)
+  {
+    int carry = -1;
+    for (int base = ((pw - 1) >> 5) << 5; base >= 0; base -= 32) {
+      const int i = base + lane;
+      const bool valid = i < pw && i <= imax && s[i] != (double)SB_NOMATCH;
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      const unsigned above = lane == 31 ? 0u : (bal & (0xffffffffu << (lane + 1)));
+      if (i < pw) nv[i] = (short)(above ? base + __ffs(above) - 1 : carry);
+      if (bal) carry = base + __ffs(bal) - 1;
+    }
+  }
+  __syncwarp();
+  const int XL1 = mt.XL, XR1 = mt.XR;
+  int carryL = XL1, carryR = XR1;
+  const uint8_t* p = mask0 + (size_t)y * W;
+  for (int base = ms.XL; base <= ms.XR; base += 32) {
+    const int x = base + lane;
+    const bool masked = x <= ms.XR && p[x] == 255;
+    bool hasL = false, hasR = false;
+    int valL = 0, valR = 0;
+    if (masked) {
+      const int t2 = (x + 1) >> 1;
+      const double sv = s[t2];
+      if (sv != (double)SB_NOMATCH) {
+        const int c = x + (int)(sv * 2 + 0.5);
+        hasL = hasR = true;
+        valL = sb_imax(c - off, XL1);
+        valR = sb_imin(c + off, XR1);
+      } else {
+        const int i = t2 < pw ? nv[t2] : -1;
+        if (i >= 0) { hasR = true; valR = sb_imin(i + (int)(s[i] * 2) + off + 1, XR1); }
+      }
+    }
+    const unsigned lower = (1u << lane) - 1;
+    const unsigned balL = __ballot_sync(0xffffffffu, hasL), balR = __ballot_sync(0xffffffffu, hasR);
+    const unsigned mL = balL & lower, mR = balR & lower;
+    const int srcL = mL ? 31 - __clz(mL) : lane, srcR = mR ? 31 - __clz(mR) : lane;
+    const int fromL = __shfl_sync(0xffffffffu, valL, srcL), fromR = __shfl_sync(0xffffffffu, valR, srcR);
+    const int bL = hasL ? valL : (mL ? fromL : carryL);
+    const int bR = hasR ? valR : (mR ? fromR : carryR);
+    if (x <= ms.XR) {
+      lo_map[(size_t)y * W + x] = (short)(masked ? bL : 1);
+      hi_map[(size_t)y * W + x] = (short)(masked ? bR : 0);
+    }
+    if (balL) carryL = __shfl_sync(0xffffffffu, valL, 31 - __clz(balL));
+    if (balR) carryR = __shfl_sync(0xffffffffu, valR, 31 - __clz(balR));
+  }
+}
+
+int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
+                      short* lo_scratch, short* hi_scratch, short* out, cudaStream_t st) {
+  (void)ph;
+  int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
+  if (ms.width <= 0 || ms.height <= 0) return n;
+  const int warps = 4;
+  k_high_ranges<<<(ms.height + warps - 1) / warps, warps * 32, warps * pw * sizeof(short), st>>>(
+      v.mask0, v.W, ms, mt, offset, prev, pw, lo_scratch, hi_scratch);
+  n += 1;
+  n += search_dispatch<8, SEARCH_RANGE_MAPS>(v, ms, R, 0, 0, lo_scratch, hi_scratch, out, st);
+  return n;
+}
+
+int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp, cudaStream_t st) {
+  return search_dispatch<8, SEARCH_REMATCH>(v, ms, R, 0, 0, BL, BR, disp, st);
+}
