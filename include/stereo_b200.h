@@ -141,7 +141,12 @@ SB200_API int64_t sb200_launch_count(const sb200_ctx* ctx);
  * sb200_set_profiling(ctx, 1); adds an event pair around each stage. */
 SB200_API int sb200_set_profiling(sb200_ctx* ctx, int enable);
 SB200_API int sb200_get_stage_ms(sb200_ctx* ctx, double* ms16, int reset);
-/* Counters of the refinement kernel: [0] = table hits, [1] = exact on-the-fly evaluations. */
+/* The dominant kernel (the DisparityRefine sweep, CStereoMatching.cpp:590-674) for the roofline line of
+ * bench.py: device time of all sweeps since the last reset (ms, CUDA events on the context stream,
+ * profiling must be enabled), the number of sweeps, and the algorithmic pixel-iterations they covered
+ * (sweeps x margin.width x margin.height; 22 algorithmic bytes each). */
+SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset);
+/* Counters of the refinement kernel: [0] unused, [1] = out-of-table (re-based) pixel evaluations. */
 SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
 
 /* glibc-compatible exp() used by the refinement weights (see DESIGN.md "exp"); host twin of the

@@ -63,6 +63,7 @@ struct sb200_ctx {
   struct Ev { int stage; cudaEvent_t a, b; };
   std::vector<Ev> events;
   double stage_ms[16] = {0};
+  int64_t sweep_launches = 0, sweep_px_iters = 0;  // since the last sb200_get_refine_profile reset
   std::string err;
   Bound cur_margin[2];
   int cur_level = -1;
@@ -209,9 +210,24 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           RefineScratch s = c->rs;
           s.A = c->f64buf[2 * d];
           s.B = c->f64buf[2 * d + 1];
+          s.ev_begin = s.ev_end = nullptr;
+          if (c->profiling) {
+            sb200_ctx::Ev ev{};
+            ev.stage = 12;
+            cudaEventCreate(&ev.a);
+            cudaEventCreate(&ev.b);
+            s.ev_begin = ev.a; s.ev_end = ev.b;
+            c->events.push_back(ev);
+          }
           double* res = nullptr;
-          c->launches += launch_refine(make_views(c, level, d == 0), msrc[d], c->ds[d], it, c->ws, s, &res, c->st);
+          const int n = launch_refine(make_views(c, level, d == 0), msrc[d], c->ds[d], it, c->ws, s, &res, c->st);
+          if (n < 0) { c->err = "too many refinement sweeps"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
           c->dd[d] = res;
+          if (c->profiling && msrc[d].width > 2 && msrc[d].height > 2) {
+            c->sweep_launches += it;
+            c->sweep_px_iters += (int64_t)it * msrc[d].width * msrc[d].height;
+          }
         }
         c->elem = 8;
       }
@@ -320,6 +336,10 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(dalloc(&c->rs.table, (size_t)SB_REFINE_K * n + pad));
   CK(dalloc(&c->rs.code, n + pad));
   CK(dalloc(&c->rs.counters, 2));
+  CK(dalloc(&c->rs.miss_count, SB_REFINE_MAX_ITERS));
+  CK(dalloc(&c->rs.miss_list, n + pad));
+  c->rs.miss_cap = (unsigned)n;
+  c->rs.ev_begin = c->rs.ev_end = nullptr;
   CK(cudaMemsetAsync(c->rs.counters, 0, 2 * sizeof(unsigned long long), c->st));
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
@@ -355,6 +375,7 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi);
   for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
   cudaFree(c->rs.table); cudaFree(c->rs.code); cudaFree(c->rs.counters);
+  cudaFree(c->rs.miss_count); cudaFree(c->rs.miss_list);
   cudaFree(c->cs.run); cudaFree(c->cs.eroded); cudaFree(c->cs.row_count); cudaFree(c->cs.row_offset);
   cudaFree(c->d_ellipse);
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
@@ -593,6 +614,18 @@ int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
   c->events.clear();
   memcpy(ms16, c->stage_ms, sizeof c->stage_ms);
   if (reset) memset(c->stage_ms, 0, sizeof c->stage_ms);
+  return SB200_OK;
+}
+
+int sb200_get_refine_profile(sb200_ctx* c, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  double ms[16];
+  int rc = sb200_get_stage_ms(c, ms, 0);
+  if (rc) return rc;
+  if (sweep_ms) *sweep_ms = ms[12];
+  if (sweep_launches) *sweep_launches = c->sweep_launches;
+  if (px_iters) *px_iters = c->sweep_px_iters;
+  if (reset) { c->stage_ms[12] = 0; c->sweep_launches = 0; c->sweep_px_iters = 0; }
   return SB200_OK;
 }
 

@@ -44,8 +44,13 @@ struct RefineScratch {
   double* B;           // W*H  pong
   double2* table;      // K_REFINE * W*H entries (pwp, c)
   unsigned short* code;  // W*H  packed (table base, mode)
-  unsigned long long* counters;  // [2]
+  unsigned long long* counters;  // [2]: [1] = out-of-table evaluations
+  unsigned* miss_count;  // [SB_REFINE_MAX_ITERS] one counter per sweep
+  unsigned* miss_list;   // [miss_cap] flat pixel indices of the current sweep's out-of-table pixels
+  unsigned miss_cap;
+  cudaEvent_t ev_begin, ev_end;  // optional: bracket the sweeps (profiling)
 };
+#define SB_REFINE_MAX_ITERS 1024
 #define SB_REFINE_K 4      // table entries per pixel: im - im0 in [-2, 1]
 #define SB_REFINE_KLO (-2)
 // Returns launches; *result receives the buffer (A or B) that holds the refined map.
