@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py — disparity Mpix/s of the stereo-matching hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C|B|small]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one camera pair per GPU: ConstructPyrm + MatchOneLayer for every
+pyramid level + DisparityToCloud (CStereoMatching.cpp:21-29), and for N > 1 the all-gather of the per-pair point
+buffers over NCCL (the one exchange step of the path).  Pairs are independent, so N GPUs process N pairs per step
+("scaling": "weak").
+
+  value   whole-job Mpix/s (N * W*H * K / time) with the rectified top-level images already in HBM
+  e2e     the same through sb200_match_pair_host (the entry the C++ CStereoMatching mirror calls): pinned host
+          images in, points out, H2D/D2H inside the timed region
+  roofline  the dominant kernel (DisparityRefine sweep): algorithmic 22 B per pixel-iteration divided
+          by its device time, measured with CUDA events on the launching stream inside the timed region
+  cpu_baseline  the reference's own CStereoMatching.cpp compiled unmodified (oracle/_ref) — or the oracle port if that
+          library is absent — on the host cores, on a bounded sample, rank 0 / N=1 only
+
+--impl reference times the reference's CPU implementation alone (same JSON shape, "impl": "reference").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "disparity Mpix/s (and 3D pts/s) at 10-view 4096x3072, 1/2/4/8 GPU vs CPU ref"
+CONFIGS = {  # name -> (pyrm_num, lowest_w, lowest_h, description)
+    "C": (5, 256, 192, "10-view 4096x3072 synthetic rig, 5-level pyramid (BASELINE.json configs[2]); one adjacent pair per GPU per step"),
+    "B": (3, 512, 384, "10-view 2048x1536 synthetic rig, 3-level pyramid (BASELINE.json configs[1]); one adjacent pair per GPU per step"),
+    "small": (3, 128, 96, "512x384 3-level smoke configuration"),
+}
+ALGO_BYTES_PER_PX_ITER = 22  # f64 in 8 + f64 out 8 + BGR 3 + 3
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm
+def cpu_run(kind, L, w0, h0, steps, warmup, threads=None):
+    """Time `steps` whole-pair runs of the CPU checker (match_pair: pyramid + all levels + cloud)."""
+    from oracle import pyoracle
+    from reconstruction_b200 import synth
+
+    sp = synth.make_pair(w0, h0, L, pair_id=0)
+    o = pyoracle.CpuStereo(kind, L, w0, h0)
+    if threads:
+        o.set_threads(threads)
+    cores = o.max_threads()
+    o.set_pair(*sp.image, *sp.mask)
+    o.set_calib(sp.Q, sp.R_final, sp.T_final)
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference printf()s its progress
+    try:
+        for _ in range(warmup):
+            o.match_pair()
+        t0 = time.perf_counter()
+        n = 0
+        for _ in range(steps):
+            n = o.match_pair()
+        dt = time.perf_counter() - t0
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+        os.close(saved)
+    W, H = sp.top_size
+    return {"mpix_s": W * H * steps / dt / 1e6, "pts_s": n * steps / dt, "sec_per_step": dt / steps, "cores": cores,
+            "sample": f"{steps} x one synthetic pair {W}x{H}, {L}-level pyramid, all stages + DisparityToCloud"}
+
+
+def pick_cpu_kind():
+    from oracle import pyoracle
+
+    try:
+        pyoracle.build()
+    except Exception as e:  # noqa: BLE001
+        log("oracle build:", e)
+    if pyoracle.available("ref"):
+        return "ref", "reference"
+    return "port", "port"
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, label = pick_cpu_kind()
+    L = CONFIGS[args.config][0]
+    total = args.steps + args.warmup
+    # bounded sample of the workload: same pyramid depth (same sweeps per level), smaller frame, sized so that the
+    # whole run stays within a few minutes (~0.05 Mpix/s on 8 cores measured in the build container)
+    ncpu = os.cpu_count() or 8
+    budget = 150.0 / max(total, 1)  # seconds per step
+    est_rate = 0.045e6 * max(ncpu, 8) / 8 * 0.6
+    w0, h0 = 32, 24
+    for cand in ((64, 48), (48, 36), (40, 30), (32, 24)):
+        px = (cand[0] << (L - 1)) * (cand[1] << (L - 1))
+        if px / est_rate <= budget:
+            w0, h0 = cand
+            break
+    r = cpu_run(kind, L, w0, h0, args.steps, args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["mpix_s"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": CONFIGS[args.config][3], "pyrm_num": L, "cpu_sample": r["sample"]},
+        "pts_per_s": r["pts_s"], "gpu_launches": 0,
+        "cpu_baseline": {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"]},
+        "e2e": {"value": r["mpix_s"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+class _DevPtr:
+    """CUDA array interface view of a raw device pointer (zero copy into torch)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+
+
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from reconstruction_b200 import capi, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the stereo path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.load()  # raises if libstereo_b200.so was not built
+
+    L, w0, h0, desc = CONFIGS[args.config]
+    W, H = w0 << (L - 1), h0 << (L - 1)
+    npx = W * H
+    t0 = time.time()
+    pairs = [synth.make_pair(w0, h0, L, pair_id=2 * rank + k) for k in range(2)]  # two inputs, alternated between steps
+    log(f"[rank {rank}] synthetic pairs {W}x{H} built in {time.time() - t0:.1f}s")
+    g = capi.StereoB200(L, w0, h0, device=local)
+    stream = torch.cuda.ExternalStream(g.stream(), device=local)
+
+    # device-resident inputs (for `value`) and pinned host inputs / outputs (for `e2e`)
+    dev_in, pin_in = [], []
+    for sp in pairs:
+        host = [torch.from_numpy(a) for a in (*sp.image, *sp.mask)]
+        pin_in.append([h.pin_memory() for h in host])
+        dev_in.append([h.cuda(local) for h in host])
+    pin_xyz = torch.empty((npx, 3), dtype=torch.float64).pin_memory()
+    pin_bgr = torch.empty((npx, 3), dtype=torch.uint8).pin_memory()
+    pin_pix = torch.empty(npx, dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    gather_bufs = {}
+
+    def exchange(n_local):
+        """All-gather of the per-pair point buffers (counts, then payload padded to the largest count)."""
+        if world == 1:
+            return 0
+        cnt = torch.tensor([n_local], dtype=torch.int64, device="cuda")
+        cnts = torch.empty(world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(cnts, cnt)
+        nmax = int(cnts.max().item())
+        xp, bp, pp, _ = g.points_device()
+        total = 0
+        for name, ptr, width in (("xyz", xp, 24), ("bgr", bp, 3), ("pix", pp, 4)):
+            src = torch.as_tensor(_DevPtr(ptr, max(nmax, 1) * width), device="cuda")
+            key = (name, nmax)
+            if key not in gather_bufs:
+                gather_bufs.clear() if len(gather_bufs) > 6 else None
+                gather_bufs[key] = torch.empty(world * max(nmax, 1) * width, dtype=torch.uint8, device="cuda")
+            dist.all_gather_into_tensor(gather_bufs[key], src)
+            total += world * nmax * width
+        return total
+
+    def step_resident(i):
+        sp = pairs[i % 2]
+        g.set_calib(sp.Q, sp.R_final, sp.T_final)
+        g.stage_device(*dev_in[i % 2])
+        n = g.match_pair()
+        exchange(n)
+        return n
+
+    def step_e2e(i):
+        sp = pairs[i % 2]
+        n = g.match_pair_host(*pin_in[i % 2], sp.Q, sp.R_final, sp.T_final, pin_xyz, pin_bgr, pin_pix, npx)
+        exchange(n)
+        return n
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, profile=False):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g.set_profiling(profile)
+        if profile:
+            g.stage_ms(reset=True)
+            g.refine_profile(reset=True)
+        launches0 = g.launch_count()
+        barrier()
+        n = 0
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for i in range(steps):
+                n = step_fn(i)
+            ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, n, g.launch_count() - launches0
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, n_pts, launches = timed(step_resident, args.steps, profile=True)
+    clocks = sampler.stop() if rank == 0 else None
+    stage_ms = g.stage_ms(reset=True)
+    top_ms, top_n, top_px = g.refine_profile(level=L - 1, reset=False)
+    all_ms, all_n, all_px = g.refine_profile(level=-1, reset=True)
+    g.set_profiling(False)
+
+    with torch.cuda.stream(stream):
+        for i in range(min(args.warmup, 2)):
+            step_e2e(i)
+    e2e_ms, n_pts_e2e, _ = timed(step_e2e, args.steps)
+
+    # totals over ranks
+    tot_pts = n_pts
+    tot_launch = launches
+    if world > 1:
+        t = torch.tensor([n_pts, launches], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        tot_pts, tot_launch = int(t[0].item()), int(t[1].item())
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        traffic, traffic_note = None, None
+        tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.exists(tpath):
+            tj = json.load(open(tpath))
+            traffic, traffic_note = tj.get("dram_bytes_per_launch"), tj.get("note")
+        achieved = ALGO_BYTES_PER_PX_ITER * top_px / (top_ms * 1e-3) / 1e9 if top_ms > 0 else None
+        achieved_all = ALGO_BYTES_PER_PX_ITER * all_px / (all_ms * 1e-3) / 1e9 if all_ms > 0 else None
+        sec = ms * 1e-3
+        out = {
+            "metric": METRIC, "value": world * npx * args.steps / sec / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "pairs_per_gpu_per_step": 1, "top_size": [W, H], "pyrm_num": L,
+                       "l2": "inputs larger than L2: ~2.4 GB working set per step, two alternating input pairs",
+                       "exchange": "all-gather of point buffers over NCCL" if world > 1 else "none (1 GPU)"},
+            "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
+            "gpu_launches": tot_launch,
+            "e2e": {"value": world * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "h2d_bytes_per_step": 4 * npx * 2, "d2h_bytes_per_step": int(n_pts_e2e) * 31,
+                    "ms_per_step": e2e_ms / args.steps, "api": "sb200_match_pair_host (pinned host buffers)"},
+            "roofline": {"bound": "hbm", "kernel": "k_refine_sweep (DisparityRefine sweep, top pyramid level)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
+                         "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX_ITER * top_px / top_n if top_n else None,
+                         "avg_launch_us": 1e3 * top_ms / top_n if top_n else None, "launches_timed": top_n,
+                         "all_levels": {"achieved": achieved_all, "frac": (achieved_all / peak) if achieved_all else None,
+                                        "launches_timed": all_n}},
+            "stage_ms_per_step": {k: round(float(stage_ms[i]) / args.steps, 4) for i, k in enumerate(
+                ["pyramid", "FindMargin", "InitialMatch", "Smooth", "Order", "Unique1", "Rematch", "Unique2", "Median", "Refine",
+                 "Unique3", "ToCloud", "RefineSweepsOnly"])},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            kind, label = pick_cpu_kind()
+            ncpu = os.cpu_count() or 8
+            w0c, h0c = (48, 36) if ncpu < 24 else (64, 48)
+            r = cpu_run(kind, L, w0c, h0c, 1, 0)
+            out["cpu_baseline"] = {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"],
+                                   "sec": r["sec_per_step"]}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--config", choices=sorted(CONFIGS), default="C")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,10 @@ SB200_API const char* sb200_status_string(int status);
  * every level on the device.  Host buffers may be pageable or pinned. */
 SB200_API int sb200_pair_upload(sb200_ctx* ctx, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0,
                       const uint8_t* mask1);
+/* Same, from buffers that already live in this GPU's memory (device pointers, same layout): the
+ * "images staged into HBM once" case of the north star; used for the device-resident bench figure. */
+SB200_API int sb200_pair_stage_device(sb200_ctx* ctx, const void* bgr0_dev, const void* bgr1_dev, const void* mask0_dev,
+                            const void* mask1_dev);
 /* Q (4x4, AFTER the sign flip at :138), R_final (3x3, :132), T_final (3, :133), row-major f64. */
 SB200_API int sb200_pair_set_calib(sb200_ctx* ctx, const double* Q, const double* R_final, const double* T_final);
 
@@ -144,8 +148,9 @@ SB200_API int sb200_get_stage_ms(sb200_ctx* ctx, double* ms16, int reset);
 /* The dominant kernel (the DisparityRefine sweep, CStereoMatching.cpp:590-674) for the roofline line of
  * bench.py: device time of all sweeps since the last reset (ms, CUDA events on the context stream,
  * profiling must be enabled), the number of sweeps, and the algorithmic pixel-iterations they covered
- * (sweeps x margin.width x margin.height; 22 algorithmic bytes each). */
-SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset);
+ * (sweeps x margin.width x margin.height; 22 algorithmic bytes each), for one pyramid
+ * level or, with level < 0, summed over all levels. */
+SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, int level, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset);
 /* Counters of the refinement kernel: [0] unused, [1] = out-of-table (re-based) pixel evaluations. */
 SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
 

@@ -25,7 +25,7 @@ STAGE_NAMES = {
 # every symbol include/stereo_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [
     "sb200_ctx_create", "sb200_ctx_destroy", "sb200_last_error", "sb200_status_string", "sb200_pair_upload",
-    "sb200_pair_set_calib", "sb200_match_pair", "sb200_match_one_layer", "sb200_run_stage", "sb200_set_refine_iters",
+    "sb200_pair_stage_device", "sb200_pair_set_calib", "sb200_match_pair", "sb200_match_one_layer", "sb200_run_stage", "sb200_set_refine_iters",
     "sb200_disparity_info", "sb200_get_disparity", "sb200_set_disparity", "sb200_get_rematch_bounds", "sb200_get_level",
     "sb200_get_margin", "sb200_triangulate", "sb200_get_points", "sb200_points_device", "sb200_match_pair_host",
     "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
@@ -67,6 +67,7 @@ def load():
         "sb200_last_error": (C.c_char_p, [vp]),
         "sb200_status_string": (C.c_char_p, [i32]),
         "sb200_pair_upload": (i32, [vp, vp, vp, vp, vp]),
+        "sb200_pair_stage_device": (i32, [vp, vp, vp, vp, vp]),
         "sb200_pair_set_calib": (i32, [vp, vp, vp, vp]),
         "sb200_match_pair": (i32, [vp, P(i64)]),
         "sb200_match_one_layer": (i32, [vp, i32]),
@@ -87,7 +88,7 @@ def load():
         "sb200_set_profiling": (i32, [vp, i32]),
         "sb200_get_stage_ms": (i32, [vp, vp, i32]),
         "sb200_get_refine_counters": (i32, [vp, vp, i32]),
-        "sb200_get_refine_profile": (i32, [vp, P(dbl), P(i64), P(i64), i32]),
+        "sb200_get_refine_profile": (i32, [vp, i32, P(dbl), P(i64), P(i64), i32]),
         "sb200_exp_host": (dbl, [dbl]),
     }
     for name, (res, args) in protos.items():
@@ -152,6 +153,11 @@ class StereoB200:
     # ---- staging ----------------------------------------------------------
     def set_pair(self, img0, img1, mask0, mask1):
         self._ck(self.lib.sb200_pair_upload(self.h, _p(img0), _p(img1), _p(mask0), _p(mask1)), "pair_upload")
+
+    def stage_device(self, img0, img1, mask0, mask1):
+        """Same as set_pair, from CUDA tensors / device pointers already resident on this GPU."""
+        ptr = [C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else C.c_void_p(int(a)) for a in (img0, img1, mask0, mask1)]
+        self._ck(self.lib.sb200_pair_stage_device(self.h, *ptr), "pair_stage_device")
 
     def set_calib(self, Q, R, T):
         q, r, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (Q, R, T))
@@ -252,10 +258,10 @@ class StereoB200:
         self._ck(self.lib.sb200_get_stage_ms(self.h, _p(out), int(reset)), "get_stage_ms")
         return out
 
-    def refine_profile(self, reset=True):
+    def refine_profile(self, level=-1, reset=True):
         """(sweep_ms, sweep_launches, px_iters) of the DisparityRefine sweep kernel since the last reset."""
         ms, n, px = C.c_double(), C.c_int64(), C.c_int64()
-        self._ck(self.lib.sb200_get_refine_profile(self.h, C.byref(ms), C.byref(n), C.byref(px), int(reset)), "get_refine_profile")
+        self._ck(self.lib.sb200_get_refine_profile(self.h, level, C.byref(ms), C.byref(n), C.byref(px), int(reset)), "get_refine_profile")
         return ms.value, n.value, px.value
 
     def refine_counters(self, reset=True):

@@ -60,10 +60,12 @@ struct sb200_ctx {
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
-  struct Ev { int stage; cudaEvent_t a, b; };
+  struct Ev { int stage; cudaEvent_t a, b; int level; };
   std::vector<Ev> events;
   double stage_ms[16] = {0};
-  int64_t sweep_launches = 0, sweep_px_iters = 0;  // since the last sb200_get_refine_profile reset
+  // DisparityRefine sweep kernel per pyramid level, since the last sb200_get_refine_profile reset
+  double sweep_ms[SB_MAX_LEVELS] = {0};
+  int64_t sweep_launches[SB_MAX_LEVELS] = {0}, sweep_px_iters[SB_MAX_LEVELS] = {0};
   std::string err;
   Bound cur_margin[2];
   int cur_level = -1;
@@ -91,6 +93,7 @@ struct StageTimer {
   StageTimer(sb200_ctx* c_, int stage) : c(c_), on(c_->profiling) {
     if (!on) return;
     ev.stage = stage;
+    ev.level = -1;
     cudaEventCreate(&ev.a);
     cudaEventCreate(&ev.b);
     cudaEventRecord(ev.a, c->st);
@@ -214,6 +217,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           if (c->profiling) {
             sb200_ctx::Ev ev{};
             ev.stage = 12;
+            ev.level = level;
             cudaEventCreate(&ev.a);
             cudaEventCreate(&ev.b);
             s.ev_begin = ev.a; s.ev_end = ev.b;
@@ -225,8 +229,8 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           c->launches += n;
           c->dd[d] = res;
           if (c->profiling && msrc[d].width > 2 && msrc[d].height > 2) {
-            c->sweep_launches += it;
-            c->sweep_px_iters += (int64_t)it * msrc[d].width * msrc[d].height;
+            c->sweep_launches[level] += it;
+            c->sweep_px_iters[level] += (int64_t)it * msrc[d].width * msrc[d].height;
           }
         }
         c->elem = 8;
@@ -384,7 +388,8 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   delete c;
 }
 
-int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1) {
+static int pair_stage(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1,
+                      cudaMemcpyKind kind) {
   if (!c || !bgr0 || !bgr1 || !mask0 || !mask1) return SB200_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
   StageTimer timer(c, 0);
@@ -393,8 +398,8 @@ int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, co
   const uint8_t* im[2] = {bgr0, bgr1};
   const uint8_t* mk[2] = {mask0, mask1};
   for (int k = 0; k < 2; k++) {
-    CK(cudaMemcpyAsync(top.img[k], im[k], npx * 3, cudaMemcpyHostToDevice, c->st));
-    CK(cudaMemcpyAsync(top.mask[k], mk[k], npx, cudaMemcpyHostToDevice, c->st));
+    CK(cudaMemcpyAsync(top.img[k], im[k], npx * 3, kind, c->st));
+    CK(cudaMemcpyAsync(top.mask[k], mk[k], npx, kind, c->st));
   }
   for (int k = 0; k < 2; k++)  // ConstructPyrm :1040-1053
     for (int i = c->L - 1; i > 0; i--) {
@@ -421,6 +426,15 @@ int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, co
   c->stats_level = -1;
   c->cur_level = -1;
   return SB200_OK;
+}
+
+int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1) {
+  return pair_stage(c, bgr0, bgr1, mask0, mask1, cudaMemcpyHostToDevice);
+}
+
+int sb200_pair_stage_device(sb200_ctx* c, const void* bgr0, const void* bgr1, const void* mask0, const void* mask1) {
+  return pair_stage(c, (const uint8_t*)bgr0, (const uint8_t*)bgr1, (const uint8_t*)mask0, (const uint8_t*)mask1,
+                    cudaMemcpyDeviceToDevice);
 }
 
 int sb200_pair_set_calib(sb200_ctx* c, const double* Q, const double* R_final, const double* T_final) {
@@ -607,7 +621,12 @@ int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
   CK(cudaStreamSynchronize(c->st));
   for (auto& e : c->events) {
     float ms = 0;
-    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 16) c->stage_ms[e.stage] += ms;
+    if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 16) {
+      c->stage_ms[e.stage] += ms;
+      if (e.stage == 12 && e.level >= 0 && e.level < SB_MAX_LEVELS) c->sweep_ms[e.level] += ms;
+    } else {
+      (void)cudaGetLastError();  // an event pair that was never recorded (no sweep ran)
+    }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
   }
@@ -617,15 +636,21 @@ int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
   return SB200_OK;
 }
 
-int sb200_get_refine_profile(sb200_ctx* c, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset) {
-  if (!c) return SB200_ERR_BAD_ARG;
+int sb200_get_refine_profile(sb200_ctx* c, int level, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset) {
+  if (!c || level >= c->L) return SB200_ERR_BAD_ARG;
   double ms[16];
   int rc = sb200_get_stage_ms(c, ms, 0);
   if (rc) return rc;
-  if (sweep_ms) *sweep_ms = ms[12];
-  if (sweep_launches) *sweep_launches = c->sweep_launches;
-  if (px_iters) *px_iters = c->sweep_px_iters;
-  if (reset) { c->stage_ms[12] = 0; c->sweep_launches = 0; c->sweep_px_iters = 0; }
+  double t = 0;
+  int64_t nl = 0, px = 0;
+  for (int l = 0; l < c->L; l++) {
+    if (level >= 0 && l != level) continue;
+    t += c->sweep_ms[l]; nl += c->sweep_launches[l]; px += c->sweep_px_iters[l];
+    if (reset) { c->sweep_ms[l] = 0; c->sweep_launches[l] = 0; c->sweep_px_iters[l] = 0; }
+  }
+  if (sweep_ms) *sweep_ms = t;
+  if (sweep_launches) *sweep_launches = nl;
+  if (px_iters) *px_iters = px;
   return SB200_OK;
 }
 
