@@ -2,6 +2,7 @@
 // stage order of MatchOneLayer (CStereoMatching.cpp:36-113) and the C entry points.
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <string>
 #include <vector>
@@ -44,8 +45,9 @@ struct sb200_ctx {
   // per-level window statistics
   double2* stats[2] = {nullptr, nullptr};
   int stats_level = -1;
-  // refinement
-  RefineScratch rs{};
+  // refinement: per-direction table / code / miss list (rs[0] also owns the counters)
+  RefineScratch rs[2]{};
+  int refine_T = 6, refine_variant = -1;  // sweeps fused per launch, tile shape (< 0: per level); SB200_REFINE_T / _TILE
   // triangulation
   CloudScratch cs{};
   short* d_ellipse = nullptr;
@@ -207,32 +209,39 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           c->launches += launch_median(c->ds[d], l.mask[d], c->ds_tmp, W, H, msrc[d], c->st);
           std::swap(c->ds[d], c->ds_tmp);
         }
-      } else {  // refine
+      } else {  // refine: both directions advance together, refine_T sweeps per launch
         const int it = c->refine_override >= 0 ? c->refine_override : 30 + level * 30;  // :95
+        RefineScratch s[2];
+        PairViews pv[2];
+        short* in[2];
         for (int d = 0; d < 2; d++) {
-          RefineScratch s = c->rs;
-          s.A = c->f64buf[2 * d];
-          s.B = c->f64buf[2 * d + 1];
-          s.ev_begin = s.ev_end = nullptr;
-          if (c->profiling) {
-            sb200_ctx::Ev ev{};
-            ev.stage = 12;
-            ev.level = level;
-            cudaEventCreate(&ev.a);
-            cudaEventCreate(&ev.b);
-            s.ev_begin = ev.a; s.ev_end = ev.b;
-            c->events.push_back(ev);
-          }
-          double* res = nullptr;
-          const int n = launch_refine(make_views(c, level, d == 0), msrc[d], c->ds[d], it, c->ws, s, &res, c->st);
-          if (n < 0) { c->err = "too many refinement sweeps"; return SB200_ERR_BAD_ARG; }
-          c->launches += n;
-          c->dd[d] = res;
-          if (c->profiling && msrc[d].width > 2 && msrc[d].height > 2) {
-            c->sweep_launches[level] += it;
-            c->sweep_px_iters[level] += (int64_t)it * msrc[d].width * msrc[d].height;
-          }
+          s[d] = c->rs[d];
+          s[d].A = c->f64buf[2 * d];
+          s[d].B = c->f64buf[2 * d + 1];
+          s[d].counters = c->rs[0].counters;
+          s[d].ev_begin = s[d].ev_end = nullptr;
+          pv[d] = make_views(c, level, d == 0);
+          in[d] = c->ds[d];
         }
+        if (c->profiling) {
+          sb200_ctx::Ev ev{};
+          ev.stage = 12;
+          ev.level = level;
+          cudaEventCreate(&ev.a);
+          cudaEventCreate(&ev.b);
+          s[0].ev_begin = ev.a; s[0].ev_end = ev.b;
+          c->events.push_back(ev);
+        }
+        double* res[2] = {nullptr, nullptr};
+        const int n = launch_refine_fused(pv, msrc, in, it, c->ws, c->refine_T, c->refine_variant, s, res, c->st);
+        if (n < 0) { c->err = "too many refinement sweeps"; return SB200_ERR_BAD_ARG; }
+        c->launches += n;
+        for (int d = 0; d < 2; d++) {
+          c->dd[d] = res[d];
+          if (c->profiling && msrc[d].width > 2 && msrc[d].height > 2)
+            c->sweep_px_iters[level] += (int64_t)it * msrc[d].width * msrc[d].height;
+        }
+        if (c->profiling) c->sweep_launches[level] += (it + c->refine_T - 1) / c->refine_T;
         c->elem = 8;
       }
       break;
@@ -337,14 +346,20 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(dalloc(&c->range_lo, n + pad));
   CK(dalloc(&c->range_hi, n + pad));
   for (int k = 0; k < 4; k++) CK(dalloc(&c->f64buf[k], n + pad));
-  CK(dalloc(&c->rs.table, (size_t)SB_REFINE_K * n + pad));
-  CK(dalloc(&c->rs.code, n + pad));
-  CK(dalloc(&c->rs.counters, 2));
-  CK(dalloc(&c->rs.miss_count, SB_REFINE_MAX_ITERS));
-  CK(dalloc(&c->rs.miss_list, n + pad));
-  c->rs.miss_cap = (unsigned)n;
-  c->rs.ev_begin = c->rs.ev_end = nullptr;
-  CK(cudaMemsetAsync(c->rs.counters, 0, 2 * sizeof(unsigned long long), c->st));
+  for (int d = 0; d < 2; d++) {
+    CK(dalloc(&c->rs[d].table, (size_t)SB_REFINE_K * n + pad));
+    CK(dalloc(&c->rs[d].code, n + pad));
+    CK(dalloc(&c->rs[d].miss_count, SB_REFINE_MAX_ITERS));
+    CK(dalloc(&c->rs[d].miss_list, n + pad));
+    c->rs[d].miss_cap = (unsigned)n;
+    c->rs[d].ev_begin = c->rs[d].ev_end = nullptr;
+  }
+  CK(dalloc(&c->rs[0].counters, 2));
+  c->rs[1].counters = c->rs[0].counters;
+  CK(cudaMemsetAsync(c->rs[0].counters, 0, 2 * sizeof(unsigned long long), c->st));
+  if (const char* e = getenv("SB200_REFINE_T")) c->refine_T = atoi(e) > 0 ? atoi(e) : c->refine_T;
+  if (const char* e = getenv("SB200_REFINE_TILE")) c->refine_variant = atoi(e);
+  if (c->refine_variant > 7) c->refine_variant = -1;
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
   CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));
@@ -378,8 +393,8 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); }
   cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi);
   for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
-  cudaFree(c->rs.table); cudaFree(c->rs.code); cudaFree(c->rs.counters);
-  cudaFree(c->rs.miss_count); cudaFree(c->rs.miss_list);
+  for (int d = 0; d < 2; d++) { cudaFree(c->rs[d].table); cudaFree(c->rs[d].code); cudaFree(c->rs[d].miss_count); cudaFree(c->rs[d].miss_list); }
+  cudaFree(c->rs[0].counters);
   cudaFree(c->cs.run); cudaFree(c->cs.eroded); cudaFree(c->cs.row_count); cudaFree(c->cs.row_offset);
   cudaFree(c->d_ellipse);
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
@@ -659,9 +674,9 @@ int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->st));
   unsigned long long h[2];
-  CK(cudaMemcpy(h, c->rs.counters, sizeof h, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h, c->rs[0].counters, sizeof h, cudaMemcpyDeviceToHost));
   out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
-  if (reset) CK(cudaMemset(c->rs.counters, 0, sizeof h));
+  if (reset) CK(cudaMemset(c->rs[0].counters, 0, sizeof h));
   return SB200_OK;
 }
 

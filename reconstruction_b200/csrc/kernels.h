@@ -53,9 +53,32 @@ struct RefineScratch {
 #define SB_REFINE_MAX_ITERS 1024
 #define SB_REFINE_K 4      // table entries per pixel: im - im0 in [-2, 1]
 #define SB_REFINE_KLO (-2)
-// Returns launches; *result receives the buffer (A or B) that holds the refined map.
-int launch_refine(const PairViews& v, Bound ms, const short* in, int iterations, double ws, const RefineScratch& s,
-                  double** result, cudaStream_t st);
+// Fused form: both matching directions advance T sweeps per launch (temporal blocking in shared memory).
+struct RefineFusedDir {
+  const uint8_t *img0, *img1;  // source / target image of this direction
+  long img_bytes;
+  Bound ms;                    // source margin
+  const double* src;
+  double* dst;
+  const double2* table;
+  const unsigned short* code;
+  double2* table_rw;           // same buffers, writable (k_refine_rebase only)
+  unsigned short* code_rw;
+  unsigned* miss_count;        // counter of this launch
+  unsigned* miss_list;
+  unsigned miss_cap;
+};
+struct RefineFusedArgs {
+  RefineFusedDir d[2];
+  int W, H, T;
+  long n_px;
+  double ws;
+  unsigned long long* counters;
+};
+// variant: tile shape / table access, see k_refine_dims in refine.cu; < 0 = pick per level.
+// s[d].A / s[d].B / table / code / miss_* are per direction; s[0].ev_begin/ev_end bracket the sweeps.
+int launch_refine_fused(const PairViews v[2], const Bound ms[2], short* const in[2], int iterations, double ws, int T,
+                        int variant, const RefineScratch s[2], double* result[2], cudaStream_t st);
 
 // K10 DisparityToCloud<double> (:682-761)
 struct CloudScratch {
