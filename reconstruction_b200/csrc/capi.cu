@@ -47,7 +47,7 @@ struct sb200_ctx {
   int stats_level = -1;
   // refinement: per-direction table / code / miss list (rs[0] also owns the counters)
   RefineScratch rs[2]{};
-  int refine_T = 6, refine_variant = -1;  // sweeps fused per launch, tile shape (< 0: per level); SB200_REFINE_T / _TILE
+  int refine_T = 5, refine_variant = -1;  // sweeps fused per launch, tile shape (< 0: per level); SB200_REFINE_T / _TILE
   // triangulation
   CloudScratch cs{};
   short* d_ellipse = nullptr;
@@ -359,7 +359,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(cudaMemsetAsync(c->rs[0].counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_REFINE_T")) c->refine_T = atoi(e) > 0 ? atoi(e) : c->refine_T;
   if (const char* e = getenv("SB200_REFINE_TILE")) c->refine_variant = atoi(e);
-  if (c->refine_variant > 7) c->refine_variant = -1;
+  if (c->refine_variant > 9) c->refine_variant = -1;
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
   CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));

@@ -1,4 +1,4 @@
 set -x
 cd /root/repo
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 900 python tools/sweep_refine.py 5 256 192 "5:0,5:1,5:2,5:4,5:5,5:6,3:0,6:0,10:0,10:1,6:4" 2>&1 | tail -20
+timeout 900 python tools/sweep_refine.py 5 256 192 "5:0,5:8,5:9,6:8" 2>&1 | tail -20
+timeout 600 python tools/time_stages.py 5 256 192 2 2>&1 | tail -22
