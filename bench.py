@@ -12,8 +12,9 @@ buffers over NCCL (the one exchange step of the path).  Pairs are independent, s
   value   whole-job Mpix/s (N * W*H * K / time) with the rectified top-level images already in HBM
   e2e     the same through sb200_match_pair_host (the entry the C++ CStereoMatching mirror calls): pinned host
           images in, points out, H2D/D2H inside the timed region
-  roofline  the dominant kernel (DisparityRefine sweep): algorithmic 22 B per pixel-iteration divided
-          by its device time, measured with CUDA events on the launching stream inside the timed region
+  roofline  the dominant kernel (DisparityRefine, k_refine_fused: one launch = several sweeps of both directions):
+          algorithmic 22 B per pixel-iteration x the pixel-iterations one launch covers, divided by its
+          average device time, measured with CUDA events on the launching stream inside the timed region
   cpu_baseline  the reference's own CStereoMatching.cpp compiled unmodified (oracle/_ref) — or the oracle port if that
           library is absent — on the host cores, on a bounded sample, rank 0 / N=1 only
 
@@ -145,12 +146,12 @@ def run_reference(args):
     L = CONFIGS[args.config][0]
     total = args.steps + args.warmup
     # bounded sample of the workload: same pyramid depth (same sweeps per level), smaller frame, sized so that the
-    # whole run stays within a few minutes (~0.05 Mpix/s on 8 cores measured in the build container)
+    # whole run stays within a few minutes (0.24 Mpix/s measured on the GPU box's 16 host threads; half of that assumed)
     ncpu = os.cpu_count() or 8
     budget = 150.0 / max(total, 1)  # seconds per step
-    est_rate = 0.045e6 * max(ncpu, 8) / 8 * 0.6
+    est_rate = 0.06e6 * max(ncpu, 8) / 8
     w0, h0 = 32, 24
-    for cand in ((64, 48), (48, 36), (40, 30), (32, 24)):
+    for cand in ((96, 72), (80, 60), (64, 48), (48, 36), (40, 30), (32, 24)):
         px = (cand[0] << (L - 1)) * (cand[1] << (L - 1))
         if px / est_rate <= budget:
             w0, h0 = cand
@@ -170,11 +171,11 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
-class _DevPtr:
+class _DevArr:
     """CUDA array interface view of a raw device pointer (zero copy into torch)."""
 
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3}
 
 
 def run_ours(args):
@@ -183,6 +184,7 @@ def run_ours(args):
     import torch.distributed as dist
 
     from reconstruction_b200 import capi, synth
+    from reconstruction_b200 import exchange as xchg
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -220,24 +222,15 @@ def run_ours(args):
     gather_bufs = {}
 
     def exchange(n_local):
-        """All-gather of the per-pair point buffers (counts, then payload padded to the largest count)."""
+        """All-gather of the per-pair point buffers over NCCL (reconstruction_b200/exchange.py)."""
         if world == 1:
             return 0
-        cnt = torch.tensor([n_local], dtype=torch.int64, device="cuda")
-        cnts = torch.empty(world, dtype=torch.int64, device="cuda")
-        dist.all_gather_into_tensor(cnts, cnt)
-        nmax = int(cnts.max().item())
         xp, bp, pp, _ = g.points_device()
-        total = 0
-        for name, ptr, width in (("xyz", xp, 24), ("bgr", bp, 3), ("pix", pp, 4)):
-            src = torch.as_tensor(_DevPtr(ptr, max(nmax, 1) * width), device="cuda")
-            key = (name, nmax)
-            if key not in gather_bufs:
-                gather_bufs.clear() if len(gather_bufs) > 6 else None
-                gather_bufs[key] = torch.empty(world * max(nmax, 1) * width, dtype=torch.uint8, device="cuda")
-            dist.all_gather_into_tensor(gather_bufs[key], src)
-            total += world * nmax * width
-        return total
+        xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
+        bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
+        pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
+        cnts, _, _, _ = xchg.allgather_points(xyz, bgr, pix, n_local, out=gather_bufs)
+        return int(cnts.max()) * world * xchg.POINT_BYTES
 
     def step_resident(i):
         sp = pairs[i % 2]
@@ -332,7 +325,7 @@ def run_ours(args):
             "e2e": {"value": world * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
                     "h2d_bytes_per_step": 4 * npx * 2, "d2h_bytes_per_step": int(n_pts_e2e) * 31,
                     "ms_per_step": e2e_ms / args.steps, "api": "sb200_match_pair_host (pinned host buffers)"},
-            "roofline": {"bound": "hbm", "kernel": "k_refine_sweep (DisparityRefine sweep, top pyramid level)",
+            "roofline": {"bound": "hbm", "kernel": "k_refine_fused (DisparityRefine: one launch = several Jacobi sweeps of both matching directions, top pyramid level)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX_ITER * top_px / top_n if top_n else None,
@@ -347,7 +340,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu:
             kind, label = pick_cpu_kind()
             ncpu = os.cpu_count() or 8
-            w0c, h0c = (48, 36) if ncpu < 24 else (64, 48)
+            w0c, h0c = (64, 48) if ncpu < 16 else (96, 72)  # ~10-30 s of CPU work
             r = cpu_run(kind, L, w0c, h0c, 1, 0)
             out["cpu_baseline"] = {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"],
                                    "sec": r["sec_per_step"]}

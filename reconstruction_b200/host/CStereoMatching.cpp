@@ -1,0 +1,211 @@
+#include "CStereoMatching.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <chrono>
+#include <mutex>
+#include <thread>
+
+#include "../../include/stereo_b200.h"
+
+struct CStereoMatching::PairResult {
+  bool ok = false;
+  int status = 0;
+  std::string error;
+  sbcv::Mat Q, Rf, Tf;
+  Boundary margin[2];
+  std::vector<double> xyz;
+  std::vector<unsigned char> bgr;
+  int64_t n = 0;
+};
+
+void CStereoMatching::Init(CManageData* data, CCloudOptimization* CloudOptimization, int radii, double ws, int disparity_offset) {
+  m_data = data;
+  m_CloudOptimization = CloudOptimization;
+  MatchBlockRadius = radii;
+  m_ws = ws;
+  m_offset = disparity_offset;
+  Verbose = 1;
+}
+
+static std::string staged_name(const std::string& root, int pair, const char* what) {
+  char b[64];
+  snprintf(b, sizeof b, "staged/pair%d%s", pair, what);
+  return root + b;
+}
+
+// The reference's Rectify (CStereoMatching.cpp:117-168) is OpenCV arithmetic end to end (stereoRectify,
+// initUndistortRectifyMap, remap, erode) and sits before the parity boundary.  The mirror reads what
+// Rectify leaves behind from <filepath>staged/, written once per data set by tools/stage_rig.py:
+//   pairN.yml            Q (after the sign flip at :138), R_final, T_final, P0, P1
+//   pairN_view{0,1}.ppm  rectified top-level colour images      pairN_mask{0,1}.pgm  rectified + eroded masks
+bool CStereoMatching::Rectify(int CamPair, sbcv::Mat& Qo, sbcv::Mat& Rf, sbcv::Mat& Tf) {
+  if (Verbose >= 1) printf("\trectifying...\n");
+  std::vector<camera>& cur = m_data->cam[CamPair];
+  const sbcv::Size largest = m_data->m_LowestLevelSize * (1 << (m_data->m_PyrmNum - 1));
+  sbcv::FileStorage fs(staged_name(m_data->m_FilePath, CamPair, ".yml"), sbcv::FileStorage::READ);
+  if (!fs.isOpened()) {
+    printf("read staged calibration %s error\n", staged_name(m_data->m_FilePath, CamPair, ".yml").c_str());
+    return false;
+  }
+  fs["Q"] >> Qo;
+  fs["R_final"] >> Rf;
+  fs["T_final"] >> Tf;
+  fs["P0"] >> cur[0].P;
+  fs["P1"] >> cur[1].P;
+  if (Qo.empty() || Qo.rows != 4 || Qo.cols != 4 || Rf.empty() || Rf.rows * Rf.cols != 9 || Tf.empty() || Tf.rows * Tf.cols != 3) {
+    printf("staged calibration of pair %d is malformed\n", CamPair);
+    return false;
+  }
+  for (int j = 0; j < 2; j++) {
+    char suffix[32];
+    snprintf(suffix, sizeof suffix, "_view%d.ppm", j);
+    if (!sbcv::imread_pnm(staged_name(m_data->m_FilePath, CamPair, suffix), cur[j].image, false)) {
+      printf("read image %s error\n", staged_name(m_data->m_FilePath, CamPair, suffix).c_str());
+      return false;
+    }
+    snprintf(suffix, sizeof suffix, "_mask%d.pgm", j);
+    if (!sbcv::imread_pnm(staged_name(m_data->m_FilePath, CamPair, suffix), cur[j].mask, true)) {
+      printf("read image %s error\n", staged_name(m_data->m_FilePath, CamPair, suffix).c_str());
+      return false;
+    }
+    if (cur[j].image.cols != largest.width || cur[j].image.rows != largest.height || cur[j].mask.cols != largest.width ||
+        cur[j].mask.rows != largest.height) {
+      printf("staged pair %d view %d is %dx%d, expected %dx%d (LowestLevelSize << (PyrmNum-1))\n", CamPair, j, cur[j].image.cols,
+             cur[j].image.rows, largest.width, largest.height);
+      return false;
+    }
+  }
+  return true;
+}
+
+bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
+  if (!Rectify(CamPair, r.Q, r.Rf, r.Tf)) {
+    r.status = SB200_ERR_BAD_ARG;
+    r.error = "Rectify failed";
+    return false;
+  }
+  std::vector<camera>& cur = m_data->cam[CamPair];
+  const size_t cap = (size_t)cur[0].image.rows * cur[0].image.cols;
+  r.xyz.resize(3 * cap);
+  r.bgr.resize(3 * cap);
+  // ConstructPyrm, MatchOneLayer x PyrmNum and DisparityToCloud (CStereoMatching.cpp:21-29) on the device
+  int rc = sb200_match_pair_host(ctx, cur[0].image.data, cur[1].image.data, cur[0].mask.data, cur[1].mask.data, r.Q.ptr<double>(),
+                                 r.Rf.ptr<double>(), r.Tf.ptr<double>(), r.xyz.data(), r.bgr.data(), nullptr, (int64_t)cap, &r.n);
+  if (rc != SB200_OK) {
+    r.status = rc;
+    r.error = std::string(sb200_status_string(rc)) + ": " + sb200_last_error(ctx);
+    return false;
+  }
+  r.xyz.resize(3 * (size_t)r.n);
+  r.bgr.resize(3 * (size_t)r.n);
+  for (int k = 0; k < 2; k++) {  // margin[k] of the top level (:27-28)
+    sb200_boundary b;
+    sb200_get_margin(ctx, m_data->m_PyrmNum - 1, k, &b);
+    r.margin[k] = Boundary{b.YL, b.YR, b.XL, b.XR, b.width, b.height};
+  }
+  r.ok = true;
+  return true;
+}
+
+void CStereoMatching::MatchAllLayer() {
+  last_status = 0;
+  last_error.clear();
+  std::vector<int> devs = devices;
+  if (devs.empty()) {
+    if (const char* e = getenv("SB200_DEVICES")) {
+      for (const char* p = e; *p;) {
+        devs.push_back(atoi(p));
+        const char* c = strchr(p, ',');
+        if (!c) break;
+        p = c + 1;
+      }
+    }
+  }
+  const int P = m_data->m_CampairNum;
+  const int L = m_data->m_PyrmNum;
+  // contexts: one per device; without an explicit list, add devices until creation fails
+  std::vector<sb200_ctx*> ctxs;
+  for (int i = 0; devs.empty() ? (i < 64 && (int)ctxs.size() < P) : (i < (int)devs.size()); i++) {
+    sb200_ctx* c = nullptr;
+    const int dev = devs.empty() ? i : devs[i];
+    const int rc = sb200_ctx_create(&c, dev, L, m_data->m_LowestLevelSize.width, m_data->m_LowestLevelSize.height,
+                                    m_data->m_OriginSize.width, m_data->m_OriginSize.height, MatchBlockRadius, m_ws, m_offset);
+    if (rc != SB200_OK) {
+      if (c) { last_error = sb200_last_error(c); sb200_ctx_destroy(c); }
+      if (devs.empty() && i > 0) break;  // ran out of devices
+      last_status = rc;
+      if (last_error.empty()) last_error = sb200_status_string(rc);
+      printf("cannot create a GPU context on device %d: %s (there is no CPU path)\n", dev, last_error.c_str());
+      for (sb200_ctx* x : ctxs) sb200_ctx_destroy(x);
+      return;
+    }
+    ctxs.push_back(c);
+  }
+  const int G = (int)ctxs.size();
+  std::vector<PairResult> results(P);
+  const auto t0 = std::chrono::steady_clock::now();
+  if (G == 1) {
+    for (int p = 0; p < P; p++) {
+      printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
+      RunPair(ctxs[0], p, results[p]);
+    }
+  } else {  // pair p -> device p mod G; each worker owns its context
+    std::mutex io;
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++)
+      workers.emplace_back([&, g]() {
+        for (int p = g; p < P; p += G) {
+          { std::lock_guard<std::mutex> lk(io); printf("processing pair %d on GPU %d: cam %d and cam %d...\n", p + 1, g, m_data->cam[p][0].camID, m_data->cam[p][1].camID); }
+          RunPair(ctxs[g], p, results[p]);
+        }
+      });
+    for (auto& w : workers) w.join();
+  }
+  gpu_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  // hand the results to the sink in pair order: InsertPoint per point, then filter(pair) (:29-31,751)
+  for (int p = 0; p < P; p++) {
+    PairResult& r = results[p];
+    if (!r.ok) {
+      last_status = r.status;
+      last_error = r.error;
+      printf("pair %d failed: %s\n", p + 1, r.error.c_str());
+      continue;
+    }
+    Q = r.Q; R_final = r.Rf; T_final = r.Tf;
+    margin[0] = r.margin[0];
+    margin[1] = r.margin[1];
+    m_data->cam[p][0].bound = margin[0];
+    m_data->cam[p][1].bound = margin[1];
+    if (Verbose >= 1) printf("\tconverting disparity to cloud %d... %lld points\n", p, (long long)r.n);
+    if (m_CloudOptimization) m_CloudOptimization->InsertPoints(r.xyz.data(), r.bgr.data(), (size_t)r.n);
+    if (m_data->isoutput) {
+      char filename[32];
+      snprintf(filename, sizeof filename, "cloud%d.ply", p);
+      WritePlyF32(filename, r.xyz.data(), r.bgr.data(), (size_t)r.n);
+    }
+    if (m_CloudOptimization) m_CloudOptimization->filter(p);
+    r.xyz.clear(); r.xyz.shrink_to_fit();
+    r.bgr.clear(); r.bgr.shrink_to_fit();
+  }
+  if (last_ctx_) sb200_ctx_destroy(last_ctx_);
+  last_ctx_ = nullptr;
+  for (int g = 0; g < G; g++) {  // keep the context that processed the last pair for FetchPyrm
+    if (P > 0 && g == (P - 1) % G) last_ctx_ = ctxs[g]; else sb200_ctx_destroy(ctxs[g]);
+  }
+}
+
+bool CStereoMatching::FetchPyrm(int CamPair) {
+  (void)CamPair;
+  if (!last_ctx_ || !m_data->imagePyrm) return false;
+  for (int i = 0; i < m_data->m_PyrmNum; i++)
+    for (int k = 0; k < 2; k++) {
+      const int w = m_data->m_LowestLevelSize.width << i, h = m_data->m_LowestLevelSize.height << i;
+      m_data->imagePyrm[i][k].create(h, w, sbcv::SB_8UC3);
+      m_data->maskPyrm[i][k].create(h, w, sbcv::SB_8UC1);
+      if (sb200_get_level(last_ctx_, i, k, m_data->imagePyrm[i][k].data, m_data->maskPyrm[i][k].data) != SB200_OK) return false;
+    }
+  return true;
+}

@@ -1,0 +1,42 @@
+// CStereoMatching.h — host mirror of the reference's matcher class (reconstruction/CStereoMatching.h:35-69): same
+// public members and methods; the per-pair body of MatchAllLayer runs on the GPU through the C ABI
+// (include/stereo_b200.h).  One context per GPU; with several GPUs the camera pairs are dealt round-robin to one
+// worker thread per device and handed to the sink in pair order.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "CCloudOptimization.h"
+#include "CManageData.h"
+
+#define NOMATCH -10000  // CStereoMatching.h:9
+
+struct sb200_ctx;
+
+class CStereoMatching {
+ public:
+  CManageData* m_data = nullptr;
+  CCloudOptimization* m_CloudOptimization = nullptr;
+  int MatchBlockRadius = 2;
+  double m_ws = 0.5;
+  int m_offset = 2;
+  sbcv::Mat Q, R_final, T_final;  // of the pair processed last (as in the reference)
+  Boundary margin[2];
+  int Verbose = 1;
+  // Initial function, must be called first (CStereoMatching.cpp:5-13)
+  void Init(CManageData* data, CCloudOptimization* CloudOptimization, int radii = 2, double ws = 0.5, int disparity_offset = 2);
+  void MatchAllLayer();  // CStereoMatching.cpp:15-34
+
+  // --- additions of the mirror (not in the reference) ---
+  std::vector<int> devices;        // CUDA devices to use; empty = SB200_DEVICES or every visible device
+  int last_status = 0;             // sb200 status of the last failing call, 0 if none
+  std::string last_error;
+  double gpu_seconds = 0;          // wall time spent inside the C ABI (all pairs)
+  bool FetchPyrm(int CamPair);     // fill m_data->imagePyrm / maskPyrm from the device pyramid of the pair processed last
+
+ private:
+  struct PairResult;
+  bool Rectify(int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf);  // CStereoMatching.cpp:117-168 (staged form)
+  bool RunPair(sb200_ctx* ctx, int CamPair, PairResult& out);
+  sb200_ctx* last_ctx_ = nullptr;
+};

@@ -1,0 +1,54 @@
+// reconstruction <config.yml>   — CLI of the reference (reconstruction/main.cpp:5-24) on the B200 path.
+//   --dump-config <config.yml>   parse only (no GPU): print what CManageData::Init read, as JSON
+#include <stdio.h>
+#include <string.h>
+
+#include <chrono>
+
+#include "CReconstruction.h"
+
+static void dump(const CManageData& d) {
+  printf("{\"filepath\": \"%s\", \"outfilename\": \"%s\", \"isoutput\": %d, \"PyrmNum\": %d, \"LowestLevelWidth\": %d, "
+         "\"LowestLevelHeight\": %d, \"OriginWidth\": %d, \"OriginHeight\": %d, \"CameraNum\": %d, \"pairs\": [",
+         d.m_FilePath.c_str(), d.outfilename.c_str(), d.isoutput, d.m_PyrmNum, d.m_LowestLevelSize.width, d.m_LowestLevelSize.height,
+         d.m_OriginSize.width, d.m_OriginSize.height, d.m_CameraNum);
+  for (int i = 0; i < d.m_CampairNum; i++) {
+    printf("%s{", i ? ", " : "");
+    for (int k = 0; k < 2; k++) {
+      const camera& c = d.cam[i][k];
+      printf("%s\"cam%d\": {\"id\": %d, \"image\": \"%s\", \"mask\": \"%s\", \"K\": [", k ? ", " : "", k, c.camID, c.image_name.c_str(),
+             c.mask_name.c_str());
+      for (int r = 0; r < 9; r++) printf("%s%.17g", r ? ", " : "", c.MatIntrinsics.ptr<double>()[r]);
+      printf("], \"Rt\": [");
+      for (int r = 0; r < 12; r++) printf("%s%.17g", r ? ", " : "", c.MatExtrinsics.ptr<double>()[r]);
+      printf("], \"center\": [%.17g, %.17g, %.17g]}", c.CamCenter.ptr<double>()[0], c.CamCenter.ptr<double>()[1], c.CamCenter.ptr<double>()[2]);
+    }
+    printf("}");
+  }
+  printf("]}\n");
+}
+
+int main(int Argc, char** Argv) {
+  const auto start = std::chrono::steady_clock::now();
+  auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); };
+  CReconstrction recon;
+  if (Argc <= 1) {
+    printf("USAGE: reconstruction your_config_file.yml\n");
+    return -1;
+  }
+  if (Argc >= 3 && strcmp(Argv[1], "--dump-config") == 0) {
+    if (recon.Init(Argv[2]) == false) return -1;
+    dump(recon.m_ImageData);
+    return 0;
+  }
+  if (recon.Init(Argv[1]) == false) return -1;
+  recon.m_Matching.MatchAllLayer();
+  printf("Matching time: %.3f s (GPU path %.3f s)\n", elapsed(), recon.m_Matching.gpu_seconds);
+  if (recon.m_Matching.last_status != 0) {
+    printf("matching failed: %s\n", recon.m_Matching.last_error.c_str());
+    return 1;
+  }
+  recon.m_CloudOptimization.run();
+  printf("total time: %.3f s\n", elapsed());
+  return 0;
+}

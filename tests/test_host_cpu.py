@@ -1,0 +1,68 @@
+"""Host mirror (reconstruction_b200/host) on CPU: it builds, parses the reference's config.yml / calib schema
+(CManageData.cpp:26-66) and refuses to run without a GPU (no CPU fallback behind the C ABI)."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from reconstruction_b200 import capi, stage
+
+HOST = os.path.join(os.path.dirname(capi.HERE), "reconstruction_b200", "host")
+BIN = os.path.join(HOST, "reconstruction")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    return BIN
+
+
+@pytest.mark.parametrize("block_style", [True, False])
+def test_config_parse(cli, tmp_path, block_style):
+    cfg, pairs = stage.write_dataset(str(tmp_path), 3, 32, 24, n_pairs=3, origin_scale=1.5, block_style=block_style)
+    d = json.loads(subprocess.run([cli, "--dump-config", cfg], check=True, capture_output=True, text=True).stdout)
+    assert (d["PyrmNum"], d["LowestLevelWidth"], d["LowestLevelHeight"]) == (3, 32, 24)
+    assert (d["OriginWidth"], d["OriginHeight"]) == pairs[0].origin_size
+    assert d["CameraNum"] == 4 and len(d["pairs"]) == 3 and d["isoutput"] == 0
+    cams = stage.rig_cameras(4, *pairs[0].origin_size)
+    for p, pr in enumerate(d["pairs"]):
+        for k in (0, 1):
+            c = pr[f"cam{k}"]
+            assert c["id"] == p + k
+            assert c["image"].endswith(f"0001_Cam{p + k}.ppm") and c["mask"].endswith(f"mask/0001_Cam{p + k}.ppm")
+            K, Rt = cams[p + k]
+            assert np.array_equal(np.array(c["K"]).reshape(3, 3), K)  # repr() round-trips doubles exactly
+            assert np.array_equal(np.array(c["Rt"]).reshape(3, 4), Rt)
+            assert np.allclose(c["center"], -Rt[:, :3].T @ Rt[:, 3], rtol=0, atol=1e-9)  # CManageData.cpp:61
+
+
+def test_config_readable_by_opencv(tmp_path):
+    """The staged files are the dialect cv::FileStorage reads (what the reference itself would parse)."""
+    cv2 = pytest.importorskip("cv2")
+    cfg, pairs = stage.write_dataset(str(tmp_path), 2, 32, 24, n_pairs=2)
+    fs = cv2.FileStorage(cfg, cv2.FILE_STORAGE_READ)
+    assert fs.isOpened()
+    assert int(fs.getNode("PyrmNum").real()) == 2
+    assert fs.getNode("camID").mat().tolist() == [[0, 1], [1, 2]]
+    n = fs.getNode("imagelist")
+    assert [n.at(i).string() for i in range(n.size())] == [f"0001_Cam{i}.ppm" for i in range(3)]
+    st = cv2.FileStorage(os.path.join(str(tmp_path), "staged", "pair1.yml"), cv2.FILE_STORAGE_READ)
+    assert np.array_equal(st.getNode("Q").mat(), pairs[1].Q)
+
+
+def test_missing_config_and_no_gpu(cli, tmp_path):
+    r = subprocess.run([cli, str(tmp_path / "nope.yml")], capture_output=True, text=True)
+    assert r.returncode != 0 and "cannot open file" in r.stdout
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    cfg, _ = stage.write_dataset(str(tmp_path), 2, 32, 24)
+    r = subprocess.run([cli, cfg], capture_output=True, text=True)
+    assert r.returncode == 1 and "no CPU path" in r.stdout

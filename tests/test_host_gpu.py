@@ -1,0 +1,38 @@
+"""The C++ host mirror end to end on the B200: `reconstruction config.yml` (reference CLI, main.cpp:5-24) on a staged
+synthetic rig; the clouds it writes must be the oracle's points (f32-rounded as the PLY branch does,
+CStereoMatching.cpp:753-756) in the reference order, with the source colours."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from reconstruction_b200 import capi, stage
+
+pytestmark = pytest.mark.gpu
+HOST = os.path.join(os.path.dirname(capi.HERE), "reconstruction_b200", "host")
+
+
+def test_cli_matches_oracle(oracle, tmp_path):
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    L, w0, h0, n_pairs = 3, 64, 48, 3
+    cfg, pairs = stage.write_dataset(str(tmp_path), L, w0, h0, n_pairs=n_pairs, isoutput=1)
+    r = subprocess.run([os.path.join(HOST, "reconstruction"), cfg], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "Matching time" in r.stdout and "total time" in r.stdout
+    all_xyz = []
+    for p, sp in enumerate(pairs):
+        o = oracle.CpuStereo("port", L, w0, h0, *sp.origin_size)
+        o.set_pair(*sp.image, *sp.mask)
+        o.set_calib(sp.Q, sp.R_final, sp.T_final)
+        n = o.match_pair()
+        oxyz = o.to_cloud()
+        obgr, opix = o.get_point_attrs()
+        xyz, bgr = stage.read_ply_f32(str(tmp_path / f"cloud{p}.ply"))
+        assert len(xyz) == n
+        assert np.array_equal(xyz.view(np.int32), oxyz.astype(np.float32).view(np.int32)), f"pair {p}: points differ"
+        assert np.array_equal(bgr, obgr)
+        all_xyz.append(oxyz.astype(np.float32))
+    xyz, _ = stage.read_ply_f32(str(tmp_path / "out.ply"))  # the sink's merged cloud, pair order
+    assert np.array_equal(xyz.view(np.int32), np.concatenate(all_xyz).view(np.int32))
