@@ -359,7 +359,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(cudaMemsetAsync(c->rs[0].counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_REFINE_T")) c->refine_T = atoi(e) > 0 ? atoi(e) : c->refine_T;
   if (const char* e = getenv("SB200_REFINE_TILE")) c->refine_variant = atoi(e);
-  if (c->refine_variant > 9) c->refine_variant = -1;
+  if (c->refine_variant > 5) c->refine_variant = -1;
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
   CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));
