@@ -151,7 +151,8 @@ SB200_API int sb200_get_stage_ms(sb200_ctx* ctx, double* ms16, int reset);
  * (sweeps x margin.width x margin.height; 22 algorithmic bytes each), for one pyramid
  * level or, with level < 0, summed over all levels. */
 SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, int level, double* sweep_ms, int64_t* sweep_launches, int64_t* px_iters, int reset);
-/* Counters of the refinement kernel: [0] unused, [1] = out-of-table (re-based) pixel evaluations. */
+/* Counters: [0] = pixels the integer screening pass of the NCC searches left to the exact FP64 search (near ties,
+ * flat windows, wide ranges), [1] = out-of-table pixel evaluations of the refinement kernel. */
 SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
 
 /* glibc-compatible exp() used by the refinement weights (see DESIGN.md "exp"); host twin of the

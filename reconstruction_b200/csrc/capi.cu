@@ -44,6 +44,12 @@ struct sb200_ctx {
   int dw = 0, dh = 0, elem = 0;
   // per-level window statistics
   double2* stats[2] = {nullptr, nullptr};
+  int2* istats[2] = {nullptr, nullptr};
+  unsigned long long* search_counters = nullptr;  // [2]: [1] = pixels the screening pass left to the exact search
+  unsigned* search_list = nullptr;
+  unsigned* search_n = nullptr;
+  SearchScratch ss{};
+  bool screen = true;                             // SB200_SCREEN=0 disables the integer screening pass
   int stats_level = -1;
   // refinement: per-direction table / code / miss list (rs[0] also owns the counters)
   RefineScratch rs[2]{};
@@ -114,6 +120,7 @@ PairViews make_views(const sb200_ctx* c, int level, bool zeroOne) {
   v.img0 = l.img[s]; v.img1 = l.img[t];
   v.mask0 = l.mask[s]; v.mask1 = l.mask[t];
   v.stat0 = c->stats[s]; v.stat1 = c->stats[t];
+  v.istat0 = c->istats[s]; v.istat1 = c->istats[t];
   v.W = l.w; v.H = l.h;
   v.img_bytes = l.img_bytes; v.mask_bytes = l.mask_bytes;
   return v;
@@ -122,8 +129,12 @@ PairViews make_views(const sb200_ctx* c, int level, bool zeroOne) {
 int ensure_stats(sb200_ctx* c, int level) {
   if (c->stats_level == level) return SB200_OK;
   const Level& l = c->lv[level];
+  // levels whose searches are screened only need the integer map; the exact pass evaluates the few windows it
+  // touches on the spot.  Level 0 (full-range search) and unscreened configurations keep the double map.
+  const bool int_only = c->screen && c->R == 2 && level > 0;
   for (int k = 0; k < 2; k++) {
-    const int n = launch_window_stats(l.img[k], l.w, l.h, c->R, c->stats[k], c->st);
+    const int n = int_only ? launch_window_istats(l.img[k], l.w, l.h, c->istats[k], c->st)
+                           : launch_window_stats(l.img[k], l.w, l.h, c->R, c->stats[k], c->R == 2 ? c->istats[k] : nullptr, c->st);
     if (n < 0) { c->err = "unsupported MatchBlockRadius (1..3)"; return SB200_ERR_BAD_ARG; }
     c->launches += n;
   }
@@ -166,7 +177,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
         }
         for (int d = 0; d < 2; d++) {
           const int n = launch_high_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->offset, c->dd[d], c->dw,
-                                          c->dh, c->range_lo, c->range_hi, c->ds[d], c->st);
+                                          c->dh, c->range_lo, c->range_hi, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, c->st);
           if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
           c->launches += n;
         }
@@ -200,7 +211,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           if (degenerate(msrc[d])) { c->err = "degenerate margin in SetBoundary_smooth (reference exits)"; return SB200_ERR_DEGENERATE_MARGIN; }
           const PairViews v = make_views(c, level, d == 0);
           c->launches += launch_rematch_bounds(c->ds[d], v.mask0, W, H, msrc[d], mtgt[d], c->BL[d], c->BR[d], c->st);
-          const int n = launch_rematch_search(v, msrc[d], c->R, c->BL[d], c->BR[d], c->ds[d], c->st);
+          const int n = launch_rematch_search(v, msrc[d], c->R, c->BL[d], c->BR[d], c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, c->st);
           if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
           c->launches += n;
         }
@@ -341,7 +352,14 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
     CK(dalloc(&c->BL[d], n + pad));
     CK(dalloc(&c->BR[d], n + pad));
     CK(dalloc(&c->stats[d], n + pad));
+    CK(dalloc(&c->istats[d], n + pad));
   }
+  CK(dalloc(&c->search_counters, 2));
+  CK(dalloc(&c->search_list, n + pad));
+  CK(dalloc(&c->search_n, 1));
+  c->ss.list = c->search_list; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
+  CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
+  if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
   CK(dalloc(&c->ds_tmp, n + pad));
   CK(dalloc(&c->range_lo, n + pad));
   CK(dalloc(&c->range_hi, n + pad));
@@ -359,7 +377,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(cudaMemsetAsync(c->rs[0].counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_REFINE_T")) c->refine_T = atoi(e) > 0 ? atoi(e) : c->refine_T;
   if (const char* e = getenv("SB200_REFINE_TILE")) c->refine_variant = atoi(e);
-  if (c->refine_variant > 5) c->refine_variant = -1;
+  if (c->refine_variant > 7) c->refine_variant = -1;
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
   CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));
@@ -390,8 +408,8 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   for (auto& l : c->lv)
     for (int k = 0; k < 2; k++) { cudaFree(l.img[k]); cudaFree(l.mask[k]); }
   cudaFree(c->d_margins);
-  for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); }
-  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi);
+  for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); cudaFree(c->istats[d]); }
+  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi); cudaFree(c->search_counters); cudaFree(c->search_list); cudaFree(c->search_n);
   for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
   for (int d = 0; d < 2; d++) { cudaFree(c->rs[d].table); cudaFree(c->rs[d].code); cudaFree(c->rs[d].miss_count); cudaFree(c->rs[d].miss_list); }
   cudaFree(c->rs[0].counters);
@@ -675,8 +693,11 @@ int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
   CK(cudaStreamSynchronize(c->st));
   unsigned long long h[2];
   CK(cudaMemcpy(h, c->rs[0].counters, sizeof h, cudaMemcpyDeviceToHost));
-  out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
+  out2[1] = (int64_t)h[1];
   if (reset) CK(cudaMemset(c->rs[0].counters, 0, sizeof h));
+  CK(cudaMemcpy(h, c->search_counters, sizeof h, cudaMemcpyDeviceToHost));
+  out2[0] = (int64_t)h[1];
+  if (reset) CK(cudaMemset(c->search_counters, 0, sizeof h));
   return SB200_OK;
 }
 

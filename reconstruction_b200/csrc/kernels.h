@@ -6,6 +6,7 @@
 struct PairViews {  // source / target view of one matching direction (image / image_inv, :43-50)
   const uint8_t *img0, *img1, *mask0, *mask1;
   const double2 *stat0, *stat1;  // per-pixel (mean, norm) of the 5x5x3 window (WindowToVec)
+  const int2 *istat0, *istat1;   // per-pixel exact (sum, sum of squares) of the same window
   int W, H;
   long img_bytes;   // readable bytes of an image buffer (payload + slack)
   long mask_bytes;  // readable bytes of a mask buffer
@@ -16,13 +17,23 @@ int launch_pyrdown(const uint8_t* src, int W, int H, int cn, uint8_t* dst, cudaS
 // K1  FindMargin (:1011-1038): out[4] = {YL, YR, XL, XR} (device ints, initialised by the kernel).
 int launch_find_margin(const uint8_t* mask, int W, int H, int R, int* out4, cudaStream_t st);
 // per-pixel WindowToVec statistics of the (2R+1)^2*3 window centred on each pixel (CManageData.cpp:81-90)
-int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats, cudaStream_t st);
+int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats, int2* istats, cudaStream_t st);
+
+// Scratch of the screened searches (K3, K7): the pixels the integer screening pass could not settle.
+struct SearchScratch {
+  unsigned* list;                // flat pixel indices
+  unsigned* n_list;              // device counter of the current search
+  unsigned cap;
+  unsigned long long* counters;  // [2]: [1] += n_list after every search (instrumentation)
+};
+// integer-only (sum, sum of squares) map of the 5x5x3 windows
+int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStream_t st);
 
 // K2  LowestLevelInitialMatch (:170-227)
 int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st);
 // K3  HighLevelInitialMatch (:231-308): prev = refined f64 map of the coarser level (pw x ph)
 int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
-                      short* lo_scratch, short* hi_scratch, short* out, cudaStream_t st);
+                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, cudaStream_t st);
 // K4  SmoothConstraint (:370-448): in -> out (out-of-place gather formulation)
 int launch_smooth(const short* in, short* out, int W, int H, Bound m, cudaStream_t st);
 // K5  OrderConstraint (:310-368): in place
@@ -33,8 +44,9 @@ int launch_unique_f64(double* P, const double* Qm, int W, int H, Bound ms, Bound
 // K7  SetBoundary_smooth (:817-942) then the NCC search of Rematch (:499-570)
 int launch_rematch_bounds(const short* disp, const uint8_t* mask, int W, int H, Bound ms, Bound mt, short* BL, short* BR,
                           cudaStream_t st);
+// sc == nullptr: no screening pass (every candidate evaluated in exact arithmetic, statistics map required)
 int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp,
-                          cudaStream_t st);
+                          const SearchScratch* sc, cudaStream_t st);
 // K8  MedianFilter (:763-815), one iteration
 int launch_median(const short* in, const uint8_t* mask, short* out, int W, int H, Bound m, cudaStream_t st);
 

@@ -100,11 +100,168 @@ __global__ void __launch_bounds__(256) k_ncc_search(PairViews v, Bound ms, int l
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The same exact search driven by a pixel list (what the screening pass below leaves unresolved): one group
+// of G lanes per listed pixel, groups strided over the whole list, so a cluster of wide-range pixels (hole
+// look-ahead) is spread over the GPU instead of serialising inside the block that owns their scanline segment.
+// (mean, norm) of the windows are evaluated on the spot by the same routines that fill the statistics map.
+// ------------------------------------------------------------------------------------------------
+template <int WS, int G>
+__global__ void __launch_bounds__(256) k_ncc_search_list(PairViews v, const unsigned* __restrict__ list, const unsigned* __restrict__ n_ptr,
+                                                         unsigned cap, const short* __restrict__ lo_map,
+                                                         const short* __restrict__ hi_map, short* __restrict__ disp) {
+  constexpr int R = WS / 2, N = WS * WS * 3, NG = 256 / G;
+  __shared__ double s_vec[NG][N];
+  const int W = v.W, pitch = 3 * W;
+  const long n_px = (long)W * v.H;
+  const long stat_first = (long)R * W + R, stat_last = n_px - stat_first;
+  const unsigned n = min(*n_ptr, cap);
+  const int gid = threadIdx.x / G, gl = threadIdx.x % G;
+  const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1) << ((threadIdx.x & 31) / G * G));
+  double* vec = s_vec[gid];
+  for (unsigned e = blockIdx.x * NG + gid; e < n; e += gridDim.x * NG) {
+    const long f = list[e];
+    const int y = (int)(f / W), x = (int)(f - (long)y * W);
+    const uint8_t* pl = v.img0 + 3 * (f - stat_first);  // source pixels lie inside the margin: window inside the payload
+    double meanL;
+    const double normL = window_stats_exact<WS>(pl, pitch, meanL);
+    const double yl = 1.0 / normL;
+    for (int k = gl; k < N; k += G) {
+      const int j = k / WS, i = k - j * WS;
+      vec[k] = div_by_common((double)pl[i * pitch + j] - meanL, normL, yl);
+    }
+    __syncwarp(gmask);
+    const int lo = lo_map[f], hi = hi_map[f];
+    double bv = -1.0;
+    int bi = -1;
+    for (int im = lo + gl; im <= hi; im += G) {
+      const long ft = (long)y * W + im;
+      if (ft < 0 || ft >= v.mask_bytes) continue;
+      if (v.mask1[ft] != 255) continue;
+      double val, mr;
+      if (ft >= stat_first && ft < stat_last) {
+        const uint8_t* pr = v.img1 + 3 * (ft - stat_first);
+        const double nr = window_stats_exact<WS>(pr, pitch, mr);
+        val = window_dot_exact<WS>(vec, 1, pr, pitch, mr) / nr;
+      } else {  // window leaves the payload: bounds-checked evaluation
+        const long off0 = 3 * (ft - stat_first);
+        const double nr = window_stats_checked<WS>(v.img1, off0, v.img_bytes, pitch, mr);
+        val = window_dot_checked<WS>(vec, 1, v.img1, off0, v.img_bytes, pitch, mr) / nr;
+      }
+      if (val > bv) { bv = val; bi = im; }
+    }
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(gmask, bv, o, G);
+      const int oi = __shfl_xor_sync(gmask, bi, o, G);
+      if (ov > bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) { bv = ov; bi = oi; }
+    }
+    if (gl == 0 && bi >= 0) disp[f] = (short)((unsigned short)bi - x);  // ushort temp_i; short(temp_i - x) (:271,:302)
+    __syncwarp(gmask);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Screening pass of the range-map searches (5x5 windows, at most 5 candidates per pixel — the normal case of
+// HighLevelInitialMatch, +-m_offset around twice the coarse disparity, :286-287).  The arg-max of
+// NCC = cov / (nL nR) over the candidates of one pixel is the arg-max of  key = sign(num) num^2 / varR  with the
+// EXACT integers  num = N Sum(LR) - Sum(L) Sum(R),  varR = N Sum(R^2) - Sum(R)^2  (nL is common and positive).
+// Sum(LR) comes from dp4a over byte-packed window rows; Sum(R), Sum(R^2) from the per-level integer statistics map.
+// A pixel is settled here only when the winner is unambiguous by a margin (relative 1e-4 on key, |rho| >= 1e-3)
+// that is ~10 orders of magnitude above the rounding noise of the reference's double evaluation (~1e-14), so the
+// reference's own strict-'>' scan must pick the same candidate.  Everything else — near ties, flat windows, wide
+// ranges (hole look-ahead), windows touching the buffer edge — is appended to a pixel list and evaluated by
+// k_ncc_search_list in the reference's exact arithmetic.
+// ------------------------------------------------------------------------------------------------
+template <int NWORDS>
+__device__ __forceinline__ void load_row_words(const uint8_t* __restrict__ base, long bo, unsigned (&w)[NWORDS]) {
+  const unsigned sh = ((unsigned)bo & 3u) * 8u;
+  const unsigned* __restrict__ p = reinterpret_cast<const unsigned*>(base + (bo & ~3L));  // buffers are cudaMalloc'ed + slack
+  unsigned a[NWORDS + 1];
+#pragma unroll
+  for (int i = 0; i <= NWORDS; i++) a[i] = p[i];
+#pragma unroll
+  for (int i = 0; i < NWORDS; i++) w[i] = __funnelshift_r(a[i], a[i + 1], sh);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, const short* __restrict__ lo_map,
+                                                     const short* __restrict__ hi_map, short* __restrict__ disp,
+                                                     unsigned* __restrict__ list, unsigned* __restrict__ n_list, unsigned cap) {
+  const int x = ms.XL + blockIdx.x * 128 + threadIdx.x, y = ms.YL + blockIdx.y;
+  if (x > ms.XR) return;
+  const int W = v.W;
+  const long f = (long)y * W + x;
+  if (v.mask0[f] != 255) return;
+  if (MODE == SEARCH_REMATCH && disp[f] != SB_NOMATCH) return;
+  const int lo = lo_map[f], hi = hi_map[f];
+  if (hi < lo) return;  // no candidate: the pixel keeps its value
+  const int2 sl = v.istat0[f];
+  const int varL = 75 * sl.y - sl.x * sl.x;
+  if (hi - lo > 4 || lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || varL == 0) {
+    const unsigned e = atomicAdd(n_list, 1u);
+    if (e < cap) list[e] = (unsigned)f;
+    return;
+  }
+  unsigned L[5][4], Rw[5][7];
+#pragma unroll
+  for (int r = 0; r < 5; r++) {
+    load_row_words<4>(v.img0, ((long)(y - 2 + r) * W + (x - 2)) * 3, L[r]);
+    L[r][3] &= 0x00ffffffu;  // 15 bytes per row
+    load_row_words<7>(v.img1, ((long)(y - 2 + r) * W + (lo - 2)) * 3, Rw[r]);
+  }
+  float best = -3.0e38f, second = -3.0e38f;
+  int bj = 0, nvalid = 0;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    const int im = lo + j;
+    const bool valid = im <= hi && v.mask1[(long)y * W + im] == 255;
+    const int wi = (3 * j) / 4;
+    const unsigned bs = ((3 * j) % 4) * 8;
+    unsigned slr = 0;
+#pragma unroll
+    for (int r = 0; r < 5; r++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const unsigned q = bs ? __funnelshift_r(Rw[r][wi + i], Rw[r][wi + i + 1 < 7 ? wi + i + 1 : 6], bs) : Rw[r][wi + i];
+        slr = __dp4a(L[r][i], q, slr);
+      }
+    if (valid) {
+      const int2 sr = v.istat1[(long)y * W + im];
+      const int num = 75 * (int)slr - sl.x * sr.x;
+      const int varR = 75 * sr.y - sr.x * sr.x;
+      const float fn = (float)num;
+      const float key = varR == 0 ? 0.0f : fn * fabsf(fn) / (float)varR;
+      nvalid++;
+      if (key > best) { second = best; best = key; bj = j; }
+      else if (key > second) second = key;
+    }
+  }
+  if (nvalid == 0) return;
+  const bool settled = best >= 1.0e-6f * (float)varL && (nvalid == 1 || best - second > 1.0e-4f * best);
+  if (settled) {
+    disp[f] = (short)((unsigned short)(lo + bj) - x);  // ushort temp_i; short(temp_i - x) (:271,:302)
+  } else {
+    const unsigned e = atomicAdd(n_list, 1u);
+    if (e < cap) list[e] = (unsigned)f;
+  }
+}
+
+__global__ void k_count_add(const unsigned* __restrict__ n, unsigned long long* __restrict__ total) { *total += *n; }
+
 template <int G, int MODE>
 static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, const short* lo_map, const short* hi_map,
-                           short* disp, cudaStream_t st) {
+                           short* disp, const SearchScratch* sc, cudaStream_t st) {
   if (ms.width <= 0 || ms.height <= 0) return 0;
   dim3 grid((ms.width + 255) / 256, ms.height);
+  if (R == 2 && MODE != SEARCH_LOWEST && sc) {  // screen first, exact arithmetic for what is left
+    cudaMemsetAsync(sc->n_list, 0, sizeof(unsigned), st);
+    dim3 gs((ms.width + 127) / 128, ms.height);
+    k_ncc_screen5<MODE><<<gs, 128, 0, st>>>(v, ms, lo_map, hi_map, disp, sc->list, sc->n_list, sc->cap);
+    k_ncc_search_list<5, 32><<<148 * 4, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, disp);
+    k_count_add<<<1, 1, 0, st>>>(sc->n_list, sc->counters + 1);
+    return 3;
+  }
   if (R == 2) k_ncc_search<5, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
   else if (R == 1) k_ncc_search<3, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
   else return -1;
@@ -116,7 +273,7 @@ static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, 
 // ------------------------------------------------------------------------------------------------
 int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st) {
   int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
-  n += search_dispatch<32, SEARCH_LOWEST>(v, ms, R, mt.XL, mt.XR, nullptr, nullptr, out, st);
+  n += search_dispatch<32, SEARCH_LOWEST>(v, ms, R, mt.XL, mt.XR, nullptr, nullptr, out, nullptr, st);
   return n;
 }
 
@@ -188,7 +345,7 @@ __global__ void __launch_bounds__(128) k_high_ranges(const uint8_t* __restrict__
 }
 
 int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
-                      short* lo_scratch, short* hi_scratch, short* out, cudaStream_t st) {
+                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, cudaStream_t st) {
   (void)ph;
   int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
   if (ms.width <= 0 || ms.height <= 0) return n;
@@ -196,10 +353,11 @@ int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset,
   k_high_ranges<<<(ms.height + warps - 1) / warps, warps * 32, warps * pw * sizeof(short), st>>>(
       v.mask0, v.W, ms, mt, offset, prev, pw, lo_scratch, hi_scratch);
   n += 1;
-  n += search_dispatch<8, SEARCH_RANGE_MAPS>(v, ms, R, 0, 0, lo_scratch, hi_scratch, out, st);
+  n += search_dispatch<8, SEARCH_RANGE_MAPS>(v, ms, R, 0, 0, lo_scratch, hi_scratch, out, sc, st);
   return n;
 }
 
-int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp, cudaStream_t st) {
-  return search_dispatch<8, SEARCH_REMATCH>(v, ms, R, 0, 0, BL, BR, disp, st);
+int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp,
+                          const SearchScratch* sc, cudaStream_t st) {
+  return search_dispatch<8, SEARCH_REMATCH>(v, ms, R, 0, 0, BL, BR, disp, sc, st);
 }

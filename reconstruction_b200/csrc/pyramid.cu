@@ -88,25 +88,66 @@ int launch_find_margin(const uint8_t* mask, int W, int H, int R, int* out4, cuda
 // the per-candidate work of the searches is the dot product only.
 // ------------------------------------------------------------------------------------------------
 template <int WS>
-__global__ void __launch_bounds__(256) k_window_stats(const uint8_t* __restrict__ img, int W, long n_px, double2* __restrict__ stats) {
+__global__ void __launch_bounds__(256) k_window_stats(const uint8_t* __restrict__ img, int W, long n_px, double2* __restrict__ stats,
+                                                      int2* __restrict__ istats) {
   constexpr int R = WS / 2;
   const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= n_px) return;
   const long first = (long)R * W + R, last = n_px - first;  // f in [first, last): all bytes inside the payload
-  if (f < first || f >= last) { stats[f] = make_double2(0.0, 1.0); return; }
+  if (f < first || f >= last) {
+    stats[f] = make_double2(0.0, 1.0);
+    if (istats) istats[f] = make_int2(0, 0);
+    return;
+  }
   const uint8_t* p0 = img + 3 * (f - first);
   double mean;
   const double nrm = window_stats_exact<WS>(p0, 3 * W, mean);
   stats[f] = make_double2(mean, nrm);
+  if (istats) {  // exact integer sums of the same window, for the screening pass of the searches (match.cu)
+    int S = 0, SS = 0;
+#pragma unroll
+    for (int i = 0; i < WS; i++)
+#pragma unroll
+      for (int j = 0; j < 3 * WS; j++) {
+        const int b = p0[i * 3 * W + j];
+        S += b;
+        SS += b * b;
+      }
+    istats[f] = make_int2(S, SS);
+  }
 }
 
-int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats, cudaStream_t st) {
+int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats, int2* istats, cudaStream_t st) {
   const long n = (long)W * H;
   const int grid = (int)((n + 255) / 256);
-  if (R == 2) k_window_stats<5><<<grid, 256, 0, st>>>(img, W, n, stats);
-  else if (R == 1) k_window_stats<3><<<grid, 256, 0, st>>>(img, W, n, stats);
-  else if (R == 3) k_window_stats<7><<<grid, 256, 0, st>>>(img, W, n, stats);
+  if (R == 2) k_window_stats<5><<<grid, 256, 0, st>>>(img, W, n, stats, istats);
+  else if (R == 1) k_window_stats<3><<<grid, 256, 0, st>>>(img, W, n, stats, istats);
+  else if (R == 3) k_window_stats<7><<<grid, 256, 0, st>>>(img, W, n, stats, istats);
   else return -1;
+  return 1;
+}
+
+// integer-only statistics map (levels where the searches are screened: the double map is not needed)
+__global__ void __launch_bounds__(256) k_window_istats5(const uint8_t* __restrict__ img, int W, long n_px, int2* __restrict__ istats) {
+  const long f = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_px) return;
+  const long first = 2L * W + 2, last = n_px - first;
+  if (f < first || f >= last) { istats[f] = make_int2(0, 0); return; }
+  const uint8_t* p0 = img + 3 * (f - first);
+  int S = 0, SS = 0;
+#pragma unroll
+  for (int i = 0; i < 5; i++)
+#pragma unroll
+    for (int j = 0; j < 15; j++) {
+      const int b = p0[i * 3 * W + j];
+      S += b;
+      SS += b * b;
+    }
+  istats[f] = make_int2(S, SS);
+}
+int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStream_t st) {
+  const long n = (long)W * H;
+  k_window_istats5<<<(int)((n + 255) / 256), 256, 0, st>>>(img, W, n, istats);
   return 1;
 }
 
