@@ -99,7 +99,8 @@ def test_golden_teacher_forced(lib, gold):
                 _check(g.get_disparity(d), gold[f"L{lv}_S{st}_d{d}"], f"teacher-forced level {lv} stage {st} dir {d}")
 
 
-@pytest.mark.parametrize("L,w0,h0,pair_id,scale", [(3, 64, 48, 1, 1.0), (2, 160, 120, 2, 1.5), (1, 200, 150, 4, 1.0)])
+@pytest.mark.parametrize("L,w0,h0,pair_id,scale", [(3, 64, 48, 1, 1.0), (2, 160, 120, 2, 1.5), (1, 200, 150, 4, 1.0),
+                                                   (2, 75, 51, 5, 1.0), (3, 50, 37, 7, 1.25)])  # odd widths: unaligned row pitches
 def test_live_oracle_free_running(lib, oracle, L, w0, h0, pair_id, scale):
     sp = synth.make_pair(w0, h0, L, pair_id=pair_id, origin_scale=scale)
     o = oracle.CpuStereo("port", L, w0, h0, *sp.origin_size)

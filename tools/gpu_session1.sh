@@ -1,4 +1,3 @@
 set -x
 cd /root/repo
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-timeout 900 python tools/sweep_refine.py 5 256 192 "5:1,5:0,5:4,5:6,6:6,8:6" 2>&1 | tail -8
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
