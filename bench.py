@@ -282,6 +282,9 @@ def run_ours(args):
     ms, n_pts, launches = timed(step_resident, args.steps, profile=True)
     clocks = sampler.stop() if rank == 0 else None
     stage_ms = g.stage_ms(reset=True)
+    ncc_ms = g.stage_level_ms(2, L - 1)  # HighLevelInitialMatch at the top level, both directions
+    ncc_px = int(sum(int(m[4]) * int(m[5]) for m in g.get_margins(L - 1)))
+    counters = g.refine_counters(reset=True)
     top_ms, top_n, top_px = g.refine_profile(level=L - 1, reset=False)
     all_ms, all_n, all_px = g.refine_profile(level=-1, reset=True)
     g.set_profiling(False)
@@ -332,6 +335,12 @@ def run_ours(args):
                          "avg_launch_us": 1e3 * top_ms / top_n if top_n else None, "launches_timed": top_n,
                          "all_levels": {"achieved": achieved_all, "frac": (achieved_all / peak) if achieved_all else None,
                                         "launches_timed": all_n}},
+            # the NCC cost-volume stage the north star names (HighLevelInitialMatch, top level, both directions: integer
+            # statistics + ranges + dp4a screening + exact FP64 pass): 12 algorithmic B per source-margin pixel
+            "ncc_top_level": {"ms_per_step": ncc_ms / args.steps, "pixels": ncc_px,
+                              "achieved_GBps": (12 * ncc_px * args.steps / (ncc_ms * 1e-3) / 1e9) if ncc_ms > 0 else None,
+                              "frac_of_hbm_peak": (12 * ncc_px * args.steps / (ncc_ms * 1e-3) / 1e9 / peak) if ncc_ms > 0 else None,
+                              "exact_fallback_pixels_per_step": int(counters[0]) // max(args.steps, 1)},
             "stage_ms_per_step": {k: round(float(stage_ms[i]) / args.steps, 4) for i, k in enumerate(
                 ["pyramid", "FindMargin", "InitialMatch", "Smooth", "Order", "Unique1", "Rematch", "Unique2", "Median", "Refine",
                  "Unique3", "ToCloud", "RefineSweepsOnly"])},

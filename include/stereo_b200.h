@@ -145,6 +145,9 @@ SB200_API int64_t sb200_launch_count(const sb200_ctx* ctx);
  * sb200_set_profiling(ctx, 1); adds an event pair around each stage. */
 SB200_API int sb200_set_profiling(sb200_ctx* ctx, int enable);
 SB200_API int sb200_get_stage_ms(sb200_ctx* ctx, double* ms16, int reset);
+/* The same for one stage at one pyramid level (e.g. stage 2 at the top level = the HighLevelInitialMatch NCC search,
+ * CStereoMatching.cpp:231-308, both directions). */
+SB200_API int sb200_get_stage_level_ms(sb200_ctx* ctx, int stage, int level, double* ms, int reset);
 /* The dominant kernel (the DisparityRefine sweep, CStereoMatching.cpp:590-674) for the roofline line of
  * bench.py: device time of all sweeps since the last reset (ms, CUDA events on the context stream,
  * profiling must be enabled), the number of sweeps, and the algorithmic pixel-iterations they covered

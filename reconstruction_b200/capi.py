@@ -29,7 +29,7 @@ SYMBOLS = [
     "sb200_disparity_info", "sb200_get_disparity", "sb200_set_disparity", "sb200_get_rematch_bounds", "sb200_get_level",
     "sb200_get_margin", "sb200_triangulate", "sb200_get_points", "sb200_points_device", "sb200_match_pair_host",
     "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
-    "sb200_get_refine_profile",
+    "sb200_get_refine_profile", "sb200_get_stage_level_ms",
     "sb200_exp_host",
 ]
 
@@ -89,6 +89,7 @@ def load():
         "sb200_get_stage_ms": (i32, [vp, vp, i32]),
         "sb200_get_refine_counters": (i32, [vp, vp, i32]),
         "sb200_get_refine_profile": (i32, [vp, i32, P(dbl), P(i64), P(i64), i32]),
+        "sb200_get_stage_level_ms": (i32, [vp, i32, i32, P(dbl), i32]),
         "sb200_exp_host": (dbl, [dbl]),
     }
     for name, (res, args) in protos.items():
@@ -257,6 +258,11 @@ class StereoB200:
         out = np.zeros(16, np.float64)
         self._ck(self.lib.sb200_get_stage_ms(self.h, _p(out), int(reset)), "get_stage_ms")
         return out
+
+    def stage_level_ms(self, stage, level, reset=True):
+        ms = C.c_double()
+        self._ck(self.lib.sb200_get_stage_level_ms(self.h, stage, level, C.byref(ms), int(reset)), "get_stage_level_ms")
+        return ms.value
 
     def refine_profile(self, level=-1, reset=True):
         """(sweep_ms, sweep_launches, px_iters) of the DisparityRefine sweep kernel since the last reset."""

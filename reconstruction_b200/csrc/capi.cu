@@ -71,6 +71,7 @@ struct sb200_ctx {
   struct Ev { int stage; cudaEvent_t a, b; int level; };
   std::vector<Ev> events;
   double stage_ms[16] = {0};
+  double stage_level_ms[16][SB_MAX_LEVELS] = {{0}};
   // DisparityRefine sweep kernel per pyramid level, since the last sb200_get_refine_profile reset
   double sweep_ms[SB_MAX_LEVELS] = {0};
   int64_t sweep_launches[SB_MAX_LEVELS] = {0}, sweep_px_iters[SB_MAX_LEVELS] = {0};
@@ -98,10 +99,10 @@ struct StageTimer {
   sb200_ctx* c;
   sb200_ctx::Ev ev{};
   bool on;
-  StageTimer(sb200_ctx* c_, int stage) : c(c_), on(c_->profiling) {
+  StageTimer(sb200_ctx* c_, int stage, int level = -1) : c(c_), on(c_->profiling) {
     if (!on) return;
     ev.stage = stage;
-    ev.level = -1;
+    ev.level = level;
     cudaEventCreate(&ev.a);
     cudaEventCreate(&ev.b);
     cudaEventRecord(ev.a, c->st);
@@ -149,7 +150,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
   if (level < 0 || level >= c->L) { c->err = "level out of range"; return SB200_ERR_BAD_ARG; }
   const Level& l = c->lv[level];
   const int W = l.w, H = l.h;
-  StageTimer timer(c, stage);
+  StageTimer timer(c, stage, level);
   if (stage == SB200_STAGE_FIND_MARGIN) {  // margins were reduced on the device at upload
     c->cur_margin[0] = l.margin[0];
     c->cur_margin[1] = l.margin[1];
@@ -656,6 +657,7 @@ int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 16) {
       c->stage_ms[e.stage] += ms;
+      if (e.level >= 0 && e.level < SB_MAX_LEVELS) c->stage_level_ms[e.stage][e.level] += ms;
       if (e.stage == 12 && e.level >= 0 && e.level < SB_MAX_LEVELS) c->sweep_ms[e.level] += ms;
     } else {
       (void)cudaGetLastError();  // an event pair that was never recorded (no sweep ran)
@@ -666,6 +668,16 @@ int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
   c->events.clear();
   memcpy(ms16, c->stage_ms, sizeof c->stage_ms);
   if (reset) memset(c->stage_ms, 0, sizeof c->stage_ms);
+  return SB200_OK;
+}
+
+int sb200_get_stage_level_ms(sb200_ctx* c, int stage, int level, double* ms, int reset) {
+  if (!c || !ms || stage < 0 || stage >= 16 || level < 0 || level >= SB_MAX_LEVELS) return SB200_ERR_BAD_ARG;
+  double tmp[16];
+  int rc = sb200_get_stage_ms(c, tmp, 0);
+  if (rc) return rc;
+  *ms = c->stage_level_ms[stage][level];
+  if (reset) c->stage_level_ms[stage][level] = 0;
   return SB200_OK;
 }
 

@@ -1,3 +1,4 @@
 set -x
 cd /root/repo
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
+timeout 900 python tools/sweep_refine.py 5 256 192 "5:1,5:0,5:4,5:6" 2>&1 | tail -5
