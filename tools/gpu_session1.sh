@@ -1,4 +1,2 @@
-set -x
 cd /root/repo
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -3
-timeout 900 python tools/sweep_refine.py 5 256 192 "5:1,5:0,5:4,5:6" 2>&1 | tail -5
+for v in 0 2 7 1; do for T in 5 6; do echo "tile $v T $T"; SB200_REFINE_TILE=$v SB200_REFINE_T=$T timeout 600 python tools/time_stages.py 5 256 192 2 2>&1 | grep -E "RefineSweeps"; done; done

@@ -16,9 +16,14 @@ for r in range(reps):
     t = time.time(); g.set_pair(*sp.image, *sp.mask); t1 = time.time(); n = g.match_pair(); t2 = time.time()
     print(f"rep {r}: upload {1e3*(t1-t):.1f} ms, match_pair {1e3*(t2-t1):.1f} ms, points {n}, launches {g.launch_count()}", flush=True)
 sm, sl, spx = g.refine_profile()
+lvl = [[g.stage_level_ms(st, lv, reset=False) for lv in range(L)] for st in range(13)]
 ms = g.stage_ms()
 for i, nm in enumerate(names):
     print(f"  {i:2d} {nm:22s} {ms[i]:9.3f} ms")
+print("  per level (ms): stage " + " ".join(f"L{lv:<6d}" for lv in range(L)))
+for st in list(range(2, 11)) + [12]:
+    print(f"  {st:2d} {(capi.STAGE_NAMES.get(st) or 'RefineSweeps'):22s} " + " ".join(f"{lvl[st][lv]:7.3f}" for lv in range(L)))
+print("     level totals           " + " ".join(f"{sum(lvl[st][lv] for st in range(2, 11)):7.3f}" for lv in range(L)))
 print("  total stages %.3f ms; refine out-of-table evals %d" % (ms[:12].sum(), g.refine_counters()[1]))
 if sl:
     print("  refine sweeps: %.3f ms over %d sweeps (%.1f us/sweep), %.3f G px-iter, %.1f GB/s algorithmic (22 B/px-iter)" % (sm, sl, 1e3 * sm / sl, spx / 1e9, 22 * spx / (sm * 1e-3) / 1e9))
