@@ -88,6 +88,32 @@ SB200_API int sb200_pair_stage_device(sb200_ctx* ctx, const void* bgr0_dev, cons
 /* Q (4x4, AFTER the sign flip at :138), R_final (3x3, :132), T_final (3, :133), row-major f64. */
 SB200_API int sb200_pair_set_calib(sb200_ctx* ctx, const double* Q, const double* R_final, const double* T_final);
 
+/* ---- Rectify (the step before the hot path, CStereoMatching.cpp:117-168) -------------------------------
+ * Calibration half (:121-145), host, double precision, no context needed: from the two cameras' intrinsics K (3x3) and
+ * extrinsics [R|t] (3x4) as CManageData::Init reads them (CManageData.cpp:59-60) to what the rest of the path uses.
+ * R_new[2][9] = R_new[0..1] of cv::stereoRectify(K0, 0, K1, 0, OriginSize, R, T, ..., flags 0, alpha -1, OriginSize);
+ * P_scaled[2][12] = P with rows 0-1 times scale (:143, the newCameraMatrix of initUndistortRectifyMap);
+ * P_final[2][12] = cam[pair][k].P after :145; Q after the sign flip (:138); R_final (:132); T_final (:133). */
+SB200_API int sb200_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
+                                  int lowest_w, int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q,
+                                  double* R_final, double* T_final);
+/* cv::stereoRectify alone, for pinning against OpenCV vectors. */
+SB200_API int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1,
+                                        double* R2, double* P1, double* P2, double* Q);
+/* Image half for one view (:144-158) on the device: initUndistortRectifyMap(K, 0, R_new, P_scaled, top size, CV_16SC2), remap
+ * (INTER_LINEAR) of the colour image and of the mask, erode of the mask with the 3*2^(L-1) ellipse.  src_* are the ORIGINAL
+ * frames (src_w x src_h, interleaved BGR / grey) in host memory; the results land in the context's top-level buffers
+ * (sb200_get_level reads them back).  use_given_maps != 0 skips the map computation and uses sb200_set_rectify_maps. */
+SB200_API int sb200_rectify_view(sb200_ctx* ctx, int view, const uint8_t* src_bgr, const uint8_t* src_mask, int src_w, int src_h,
+                                 const double* K, const double* R_new, const double* P_scaled, int use_given_maps);
+/* ConstructPyrm + FindMargin after both views were rectified (what sb200_pair_upload does after its copy). */
+SB200_API int sb200_pair_build(sb200_ctx* ctx);
+/* Parity hooks: the fixed-point maps of the view rectified last (map1: H*W*2 s16 = (x, y), map2: H*W u16), the remapped mask
+ * before erosion. */
+SB200_API int sb200_get_rectify_maps(sb200_ctx* ctx, int16_t* map1, uint16_t* map2);
+SB200_API int sb200_set_rectify_maps(sb200_ctx* ctx, const int16_t* map1, const uint16_t* map2);
+SB200_API int sb200_get_remapped_mask(sb200_ctx* ctx, uint8_t* out);
+
 /* ---- the hot path ------------------------------------------------------------------------------
  * MatchAllLayer's per-pair body, CStereoMatching.cpp:21-29: MatchOneLayer for every level
  * (stages 1-10) then DisparityToCloud.  Asynchronous work is finished when the call returns.

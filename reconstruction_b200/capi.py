@@ -31,6 +31,8 @@ SYMBOLS = [
     "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
     "sb200_get_refine_profile", "sb200_get_stage_level_ms",
     "sb200_exp_host",
+    "sb200_rectify_calib", "sb200_stereo_rectify_host", "sb200_rectify_view", "sb200_pair_build", "sb200_get_rectify_maps",
+    "sb200_set_rectify_maps", "sb200_get_remapped_mask",
 ]
 
 
@@ -91,6 +93,13 @@ def load():
         "sb200_get_refine_profile": (i32, [vp, i32, P(dbl), P(i64), P(i64), i32]),
         "sb200_get_stage_level_ms": (i32, [vp, i32, i32, P(dbl), i32]),
         "sb200_exp_host": (dbl, [dbl]),
+        "sb200_rectify_calib": (i32, [vp] * 4 + [i32] * 4 + [vp] * 6),
+        "sb200_stereo_rectify_host": (i32, [vp, vp, i32, i32] + [vp] * 7),
+        "sb200_rectify_view": (i32, [vp, i32, vp, vp, i32, i32, vp, vp, vp, i32]),
+        "sb200_pair_build": (i32, [vp]),
+        "sb200_get_rectify_maps": (i32, [vp, vp, vp]),
+        "sb200_set_rectify_maps": (i32, [vp, vp, vp]),
+        "sb200_get_remapped_mask": (i32, [vp, vp]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -159,6 +168,32 @@ class StereoB200:
         """Same as set_pair, from CUDA tensors / device pointers already resident on this GPU."""
         ptr = [C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else C.c_void_p(int(a)) for a in (img0, img1, mask0, mask1)]
         self._ck(self.lib.sb200_pair_stage_device(self.h, *ptr), "pair_stage_device")
+
+    # ---- Rectify (device image half) -------------------------------------------------
+    def rectify_view(self, view, src_bgr, src_mask, K=None, R_new=None, P_scaled=None, use_given_maps=False):
+        src_bgr, src_mask = np.ascontiguousarray(src_bgr, np.uint8), np.ascontiguousarray(src_mask, np.uint8)
+        mats = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (K, R_new, P_scaled)]
+        self._ck(self.lib.sb200_rectify_view(self.h, view, _p(src_bgr), _p(src_mask), src_mask.shape[1], src_mask.shape[0],
+                                             *[_p(m) for m in mats], int(use_given_maps)), "rectify_view")
+
+    def pair_build(self):
+        self._ck(self.lib.sb200_pair_build(self.h), "pair_build")
+
+    def get_rectify_maps(self):
+        w, h = self.top_size
+        m1, m2 = np.empty((h, w, 2), np.int16), np.empty((h, w), np.uint16)
+        self._ck(self.lib.sb200_get_rectify_maps(self.h, _p(m1), _p(m2)), "get_rectify_maps")
+        return m1, m2
+
+    def set_rectify_maps(self, m1, m2):
+        m1, m2 = np.ascontiguousarray(m1, np.int16), np.ascontiguousarray(m2, np.uint16)
+        self._ck(self.lib.sb200_set_rectify_maps(self.h, _p(m1), _p(m2)), "set_rectify_maps")
+
+    def get_remapped_mask(self):
+        w, h = self.top_size
+        out = np.empty((h, w), np.uint8)
+        self._ck(self.lib.sb200_get_remapped_mask(self.h, _p(out)), "get_remapped_mask")
+        return out
 
     def set_calib(self, Q, R, T):
         q, r, t = (np.ascontiguousarray(a, dtype=np.float64) for a in (Q, R, T))
@@ -274,6 +309,28 @@ class StereoB200:
         out = np.zeros(2, np.int64)
         self._ck(self.lib.sb200_get_refine_counters(self.h, _p(out), int(reset)), "get_refine_counters")
         return out
+
+
+def rectify_calib(K0, Rt0, K1, Rt1, origin, lowest_w, pyrm_num):
+    """Host half of Rectify (no GPU needed): dict with R_new [2,3,3], P_scaled [2,3,4], P_final [2,3,4], Q, R_final, T_final."""
+    a = [np.ascontiguousarray(m, np.float64) for m in (K0, Rt0, K1, Rt1)]
+    out = {"R_new": np.zeros((2, 3, 3)), "P_scaled": np.zeros((2, 3, 4)), "P_final": np.zeros((2, 3, 4)), "Q": np.zeros((4, 4)),
+           "R_final": np.zeros((3, 3)), "T_final": np.zeros(3)}
+    rc = load().sb200_rectify_calib(*[_p(m) for m in a], int(origin[0]), int(origin[1]), int(lowest_w), int(pyrm_num),
+                                    *[_p(out[k]) for k in ("R_new", "P_scaled", "P_final", "Q", "R_final", "T_final")])
+    if rc != 0:
+        raise StereoError("rectify_calib: bad argument")
+    return out
+
+
+def stereo_rectify_host(K1, K2, size, R, T):
+    a = [np.ascontiguousarray(m, np.float64) for m in (K1, K2, R, T)]
+    R1, R2, P1, P2, Q = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((4, 4))
+    rc = load().sb200_stereo_rectify_host(_p(a[0]), _p(a[1]), int(size[0]), int(size[1]), _p(a[2]), _p(a[3]), _p(R1), _p(R2), _p(P1),
+                                          _p(P2), _p(Q))
+    if rc != 0:
+        raise StereoError("stereo_rectify_host: bad argument")
+    return R1, R2, P1, P2, Q
 
 
 def exp_host(x: float) -> float:

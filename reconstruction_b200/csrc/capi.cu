@@ -65,6 +65,15 @@ struct sb200_ctx {
   int* d_npoints = nullptr;
   int* h_npoints = nullptr;  // pinned
   int64_t n_points = 0;
+  // Rectify scratch (allocated on first use)
+  uint8_t *rc_src_img = nullptr, *rc_src_mask = nullptr, *rc_tab = nullptr;
+  size_t rc_src_cap = 0;
+  short2* rc_map1 = nullptr;
+  unsigned short* rc_map2 = nullptr;
+  short* rc_ellipse = nullptr;
+  int rc_ks = 0, rc_levels = 0;
+  bool rc_maps_given = false;
+  int rc_views_done = 0;
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
@@ -416,26 +425,16 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaFree(c->rs[0].counters);
   cudaFree(c->cs.run); cudaFree(c->cs.eroded); cudaFree(c->cs.row_count); cudaFree(c->cs.row_offset);
   cudaFree(c->d_ellipse);
+  cudaFree(c->rc_src_img); cudaFree(c->rc_src_mask); cudaFree(c->rc_tab); cudaFree(c->rc_map1); cudaFree(c->rc_map2); cudaFree(c->rc_ellipse);
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
   if (c->h_npoints) cudaFreeHost(c->h_npoints);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
 
-static int pair_stage(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1,
-                      cudaMemcpyKind kind) {
-  if (!c || !bgr0 || !bgr1 || !mask0 || !mask1) return SB200_ERR_BAD_ARG;
-  CK(cudaSetDevice(c->device));
-  StageTimer timer(c, 0);
-  Level& top = c->lv[c->L - 1];
-  const size_t npx = (size_t)top.w * top.h;
-  const uint8_t* im[2] = {bgr0, bgr1};
-  const uint8_t* mk[2] = {mask0, mask1};
-  for (int k = 0; k < 2; k++) {
-    CK(cudaMemcpyAsync(top.img[k], im[k], npx * 3, kind, c->st));
-    CK(cudaMemcpyAsync(top.mask[k], mk[k], npx, kind, c->st));
-  }
-  for (int k = 0; k < 2; k++)  // ConstructPyrm :1040-1053
+// ConstructPyrm (:1040-1053) + FindMargin (:1011-1038) for every level, from the top-level buffers
+static int build_pyramid(sb200_ctx* c) {
+  for (int k = 0; k < 2; k++)
     for (int i = c->L - 1; i > 0; i--) {
       c->launches += launch_pyrdown(c->lv[i].img[k], c->lv[i].w, c->lv[i].h, 3, c->lv[i - 1].img[k], c->st);
       c->launches += launch_pyrdown(c->lv[i].mask[k], c->lv[i].w, c->lv[i].h, 1, c->lv[i - 1].mask[k], c->st);
@@ -460,6 +459,136 @@ static int pair_stage(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, co
   c->stats_level = -1;
   c->cur_level = -1;
   return SB200_OK;
+}
+
+static int pair_stage(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1,
+                      cudaMemcpyKind kind) {
+  if (!c || !bgr0 || !bgr1 || !mask0 || !mask1) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  StageTimer timer(c, 0);
+  Level& top = c->lv[c->L - 1];
+  const size_t npx = (size_t)top.w * top.h;
+  const uint8_t* im[2] = {bgr0, bgr1};
+  const uint8_t* mk[2] = {mask0, mask1};
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMemcpyAsync(top.img[k], im[k], npx * 3, kind, c->st));
+    CK(cudaMemcpyAsync(top.mask[k], mk[k], npx, kind, c->st));
+  }
+  return build_pyramid(c);
+}
+
+static int rectify_prepare(sb200_ctx* c, size_t src_px) {
+  Level& top = c->lv[c->L - 1];
+  const size_t n = (size_t)top.w * top.h;
+  if (!c->rc_map1) {
+    c->rc_ks = 3 * (1 << (c->L - 1));  // :157
+    c->rc_levels = 1;
+    while ((2 << (c->rc_levels - 1)) <= c->rc_ks) c->rc_levels++;
+    CK(dalloc(&c->rc_map1, n));
+    CK(dalloc(&c->rc_map2, n));
+    CK(dalloc(&c->rc_tab, (size_t)c->rc_levels * n));
+    std::vector<short> j12(2 * (size_t)c->rc_ks);
+    sb_ellipse_rows(c->rc_ks, j12.data(), j12.data() + c->rc_ks);
+    CK(dalloc(&c->rc_ellipse, j12.size()));
+    CK(cudaMemcpy(c->rc_ellipse, j12.data(), j12.size() * sizeof(short), cudaMemcpyHostToDevice));
+  }
+  if (src_px > c->rc_src_cap) {
+    cudaFree(c->rc_src_img); cudaFree(c->rc_src_mask);
+    c->rc_src_img = c->rc_src_mask = nullptr;
+    CK(dalloc(&c->rc_src_img, src_px * 3));
+    CK(dalloc(&c->rc_src_mask, src_px));
+    c->rc_src_cap = src_px;
+  }
+  return SB200_OK;
+}
+
+int sb200_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
+                        int lowest_w, int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final,
+                        double* T_final) {
+  if (!K0 || !Rt0 || !K1 || !Rt1 || !R_new || !P_scaled || !P_final || !Q || !R_final || !T_final || origin_w <= 0 || origin_h <= 0 ||
+      lowest_w <= 0 || pyrm_num < 1)
+    return SB200_ERR_BAD_ARG;
+  sb_rectify_calib(K0, Rt0, K1, Rt1, origin_w, origin_h, lowest_w, pyrm_num, R_new, P_scaled, P_final, Q, R_final, T_final);
+  return SB200_OK;
+}
+
+int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1,
+                              double* R2, double* P1, double* P2, double* Q) {
+  if (!K1 || !K2 || !R || !T || !R1 || !R2 || !P1 || !P2 || !Q) return SB200_ERR_BAD_ARG;
+  sb_stereo_rectify(K1, K2, nx, ny, R, T, R1, R2, P1, P2, Q);
+  return SB200_OK;
+}
+
+int sb200_set_rectify_maps(sb200_ctx* c, const int16_t* map1, const uint16_t* map2) {
+  if (!c || !map1 || !map2) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  int rc = rectify_prepare(c, 0);
+  if (rc) return rc;
+  const Level& top = c->lv[c->L - 1];
+  const size_t n = (size_t)top.w * top.h;
+  CK(cudaMemcpyAsync(c->rc_map1, map1, n * 4, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->rc_map2, map2, n * 2, cudaMemcpyHostToDevice, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  c->rc_maps_given = true;
+  return SB200_OK;
+}
+
+int sb200_get_rectify_maps(sb200_ctx* c, int16_t* map1, uint16_t* map2) {
+  if (!c || !map1 || !map2) return SB200_ERR_BAD_ARG;
+  if (!c->rc_map1) { c->err = "no view rectified yet"; return SB200_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  const Level& top = c->lv[c->L - 1];
+  const size_t n = (size_t)top.w * top.h;
+  CK(cudaMemcpyAsync(map1, c->rc_map1, n * 4, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaMemcpyAsync(map2, c->rc_map2, n * 2, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_get_remapped_mask(sb200_ctx* c, uint8_t* out) {
+  if (!c || !out) return SB200_ERR_BAD_ARG;
+  if (!c->rc_tab) { c->err = "no view rectified yet"; return SB200_ERR_STATE; }
+  CK(cudaSetDevice(c->device));
+  const Level& top = c->lv[c->L - 1];
+  CK(cudaMemcpyAsync(out, c->rc_tab, (size_t)top.w * top.h, cudaMemcpyDeviceToHost, c->st));
+  CK(cudaStreamSynchronize(c->st));
+  return SB200_OK;
+}
+
+int sb200_rectify_view(sb200_ctx* c, int view, const uint8_t* src_bgr, const uint8_t* src_mask, int src_w, int src_h, const double* K,
+                       const double* R_new, const double* P_scaled, int use_given_maps) {
+  if (!c || view < 0 || view > 1 || !src_bgr || !src_mask || src_w <= 0 || src_h <= 0) return SB200_ERR_BAD_ARG;
+  if (!use_given_maps && (!K || !R_new || !P_scaled)) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  StageTimer timer(c, 13);
+  const size_t spx = (size_t)src_w * src_h;
+  int rc = rectify_prepare(c, spx);
+  if (rc) return rc;
+  Level& top = c->lv[c->L - 1];
+  CK(cudaMemcpyAsync(c->rc_src_img, src_bgr, spx * 3, cudaMemcpyHostToDevice, c->st));
+  CK(cudaMemcpyAsync(c->rc_src_mask, src_mask, spx, cudaMemcpyHostToDevice, c->st));
+  if (use_given_maps) {
+    if (!c->rc_maps_given) { c->err = "sb200_set_rectify_maps first"; return SB200_ERR_STATE; }
+  } else {
+    RectifyView rv;
+    if (!sb_rectify_inverse(P_scaled, R_new, rv.iR)) { c->err = "singular rectification matrix"; return SB200_ERR_BAD_ARG; }
+    rv.fx = K[0]; rv.fy = K[4]; rv.u0 = K[2]; rv.v0 = K[5];
+    c->launches += launch_rectify_maps(top.w, top.h, rv, c->rc_map1, c->rc_map2, c->st);  // :144
+  }
+  c->launches += launch_remap(c->rc_src_img, src_w, src_h, 3, c->rc_map1, c->rc_map2, top.w, top.h, top.img[view], c->st);  // :154
+  c->launches += launch_remap(c->rc_src_mask, src_w, src_h, 1, c->rc_map1, c->rc_map2, top.w, top.h, c->rc_tab, c->st);    // :156
+  c->launches += launch_erode_ellipse(c->rc_tab, c->rc_levels, top.w, top.h, c->rc_ks, c->rc_ellipse, top.mask[view], c->st);  // :157-158
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->st));
+  c->uploaded = false;  // the pyramid is stale until sb200_pair_build
+  return SB200_OK;
+}
+
+int sb200_pair_build(sb200_ctx* c) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  StageTimer timer(c, 0);
+  return build_pyramid(c);
 }
 
 int sb200_pair_upload(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1, const uint8_t* mask0, const uint8_t* mask1) {
@@ -576,7 +705,8 @@ int sb200_get_rematch_bounds(sb200_ctx* c, int dir, int16_t* bl, int16_t* br) {
 
 int sb200_get_level(sb200_ctx* c, int level, int view, uint8_t* bgr_out, uint8_t* mask_out) {
   if (!c || level < 0 || level >= c->L || view < 0 || view > 1) return SB200_ERR_BAD_ARG;
-  if (!c->uploaded) { c->err = "no pair uploaded"; return SB200_ERR_STATE; }
+  // the top level is readable right after sb200_rectify_view, before the pyramid is built
+  if (!c->uploaded && !(level == c->L - 1 && c->rc_map1)) { c->err = "no pair uploaded"; return SB200_ERR_STATE; }
   CK(cudaSetDevice(c->device));
   const Level& l = c->lv[level];
   const size_t n = (size_t)l.w * l.h;

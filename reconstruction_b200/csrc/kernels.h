@@ -110,5 +110,20 @@ int launch_cloud(const double* disp, const uint8_t* mask, const uint8_t* img, in
                  const CloudParams& p, const CloudScratch& s, double* xyz, uint8_t* bgr, int* pix, int* n_points_dev,
                  cudaStream_t st);
 
+// Rectify (:117-168), see rectify.cu
+struct RectifyView {
+  double iR[9];            // (P[:, :3] * R_new)^-1
+  double fx, fy, u0, v0;   // of the ORIGINAL camera matrix
+};
+void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1, double* R2,
+                       double* P1, double* P2, double* Q);
+void sb_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h, int lowest_w,
+                      int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final, double* T_final);
+bool sb_rectify_inverse(const double* P_scaled, const double* R_new, double* iR);
+int launch_rectify_maps(int W, int H, const RectifyView& rv, short2* map1, unsigned short* map2, cudaStream_t st);
+int launch_remap(const uint8_t* src, int sw, int sh, int cn, const short2* map1, const unsigned short* map2, int W, int H, uint8_t* dst,
+                 cudaStream_t st);
+int launch_erode_ellipse(uint8_t* tab, int levels, int W, int H, int ks, const short* j12_dev, uint8_t* out, cudaStream_t st);
+
 // s16 -> f64 conversion (Mat::convertTo, :585,587) and fills
 int launch_fill_s16(short* p, long n, short v, cudaStream_t st);
