@@ -36,20 +36,63 @@ static std::string staged_name(const std::string& root, int pair, const char* wh
   return root + b;
 }
 
-// The reference's Rectify (CStereoMatching.cpp:117-168) is OpenCV arithmetic end to end (stereoRectify,
-// initUndistortRectifyMap, remap, erode) and sits before the parity boundary.  The mirror reads what
-// Rectify leaves behind from <filepath>staged/, written once per data set by tools/stage_rig.py:
-//   pairN.yml            Q (after the sign flip at :138), R_final, T_final, P0, P1
-//   pairN_view{0,1}.ppm  rectified top-level colour images      pairN_mask{0,1}.pgm  rectified + eroded masks
-bool CStereoMatching::Rectify(int CamPair, sbcv::Mat& Qo, sbcv::Mat& Rf, sbcv::Mat& Tf) {
+// Rectify (CStereoMatching.cpp:117-168).  Two sources, tried in this order:
+//  (1) NATIVE: the original frames named in config.yml (binary PNM) + the calibration of CManageData::Init: the calibration
+//      half runs on the host (sb200_rectify_calib: stereoRectify restatement), the image half on the GPU
+//      (sb200_rectify_view: initUndistortRectifyMap + remap + erode); the rectified frames stay in HBM and are copied
+//      back only to fill cam[pair][k].image / .mask for the sink.
+//  (2) STAGED: <filepath>staged/pairN.yml (Q after the sign flip, R_final, T_final, P0, P1) + pairN_view{0,1}.ppm +
+//      pairN_mask{0,1}.pgm, i.e. the RESULTS of Rectify written by reconstruction_b200/stage.py (tools/stage_rig.py).
+// On success with (1) the context already holds the pyramid (`staged_on_device`).
+bool CStereoMatching::Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Qo, sbcv::Mat& Rf, sbcv::Mat& Tf, bool& staged_on_device) {
   if (Verbose >= 1) printf("\trectifying...\n");
+  staged_on_device = false;
   std::vector<camera>& cur = m_data->cam[CamPair];
   const sbcv::Size largest = m_data->m_LowestLevelSize * (1 << (m_data->m_PyrmNum - 1));
   sbcv::FileStorage fs(staged_name(m_data->m_FilePath, CamPair, ".yml"), sbcv::FileStorage::READ);
-  if (!fs.isOpened()) {
-    printf("read staged calibration %s error\n", staged_name(m_data->m_FilePath, CamPair, ".yml").c_str());
-    return false;
+  if (!fs.isOpened()) {  // ---- (1) native ----
+    sbcv::Mat src[2], msk[2];
+    for (int j = 0; j < 2; j++) {
+      if (!sbcv::imread_pnm(cur[j].image_name, src[j], false)) {
+        printf("read image %s error\n", cur[j].image_name.c_str());  // :147-151
+        return false;
+      }
+      if (!sbcv::imread_pnm(cur[j].mask_name, msk[j], true) || msk[j].cols != src[j].cols || msk[j].rows != src[j].rows) {
+        printf("read image %s error\n", cur[j].mask_name.c_str());
+        return false;
+      }
+    }
+    double R_new[18], P_scaled[24], P_final[24];
+    Qo.create(4, 4, sbcv::SB_64FC1);
+    Rf.create(3, 3, sbcv::SB_64FC1);
+    Tf.create(3, 1, sbcv::SB_64FC1);
+    if (sb200_rectify_calib(cur[0].MatIntrinsics.ptr<double>(), cur[0].MatExtrinsics.ptr<double>(), cur[1].MatIntrinsics.ptr<double>(),
+                            cur[1].MatExtrinsics.ptr<double>(), m_data->m_OriginSize.width, m_data->m_OriginSize.height,
+                            m_data->m_LowestLevelSize.width, m_data->m_PyrmNum, R_new, P_scaled, P_final, Qo.ptr<double>(),
+                            Rf.ptr<double>(), Tf.ptr<double>()) != SB200_OK)
+      return false;
+    for (int j = 0; j < 2; j++) {
+      if (sb200_rectify_view(ctx, j, src[j].data, msk[j].data, src[j].cols, src[j].rows, cur[j].MatIntrinsics.ptr<double>(), R_new + 9 * j,
+                             P_scaled + 12 * j, 0) != SB200_OK) {
+        printf("rectification of pair %d view %d failed: %s\n", CamPair, j, sb200_last_error(ctx));
+        return false;
+      }
+      cur[j].P.create(3, 4, sbcv::SB_64FC1);
+      memcpy(cur[j].P.data, P_final + 12 * j, 12 * sizeof(double));
+      cur[j].image.create(largest.height, largest.width, sbcv::SB_8UC3);
+      cur[j].mask.create(largest.height, largest.width, sbcv::SB_8UC1);
+      if (sb200_get_level(ctx, m_data->m_PyrmNum - 1, j, cur[j].image.data, cur[j].mask.data) != SB200_OK) return false;
+      if (m_data->isoutput) {  // the reference writes "<pair>_<camID>.jpg" (:159-166); PNM here
+        char filename[64];
+        snprintf(filename, sizeof filename, "%d_%d.ppm", CamPair, cur[j].camID);
+        sbcv::imwrite_pnm(filename, cur[j].image);
+      }
+    }
+    if (sb200_pair_build(ctx) != SB200_OK) return false;
+    staged_on_device = true;
+    return true;
   }
+  // ---- (2) staged ----
   fs["Q"] >> Qo;
   fs["R_final"] >> Rf;
   fs["T_final"] >> Tf;
@@ -82,7 +125,8 @@ bool CStereoMatching::Rectify(int CamPair, sbcv::Mat& Qo, sbcv::Mat& Rf, sbcv::M
 }
 
 bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
-  if (!Rectify(CamPair, r.Q, r.Rf, r.Tf)) {
+  bool on_device = false;
+  if (!Rectify(ctx, CamPair, r.Q, r.Rf, r.Tf, on_device)) {
     r.status = SB200_ERR_BAD_ARG;
     r.error = "Rectify failed";
     return false;
@@ -92,8 +136,15 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
   r.xyz.resize(3 * cap);
   r.bgr.resize(3 * cap);
   // ConstructPyrm, MatchOneLayer x PyrmNum and DisparityToCloud (CStereoMatching.cpp:21-29) on the device
-  int rc = sb200_match_pair_host(ctx, cur[0].image.data, cur[1].image.data, cur[0].mask.data, cur[1].mask.data, r.Q.ptr<double>(),
-                                 r.Rf.ptr<double>(), r.Tf.ptr<double>(), r.xyz.data(), r.bgr.data(), nullptr, (int64_t)cap, &r.n);
+  int rc;
+  if (on_device) {  // frames were rectified in HBM, the pyramid is built: match and fetch the points
+    rc = sb200_pair_set_calib(ctx, r.Q.ptr<double>(), r.Rf.ptr<double>(), r.Tf.ptr<double>());
+    if (rc == SB200_OK) rc = sb200_match_pair(ctx, &r.n);
+    if (rc == SB200_OK) rc = sb200_get_points(ctx, r.xyz.data(), r.bgr.data(), nullptr);
+  } else {
+    rc = sb200_match_pair_host(ctx, cur[0].image.data, cur[1].image.data, cur[0].mask.data, cur[1].mask.data, r.Q.ptr<double>(),
+                               r.Rf.ptr<double>(), r.Tf.ptr<double>(), r.xyz.data(), r.bgr.data(), nullptr, (int64_t)cap, &r.n);
+  }
   if (rc != SB200_OK) {
     r.status = rc;
     r.error = std::string(sb200_status_string(rc)) + ": " + sb200_last_error(ctx);

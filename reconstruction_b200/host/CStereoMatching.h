@@ -36,7 +36,7 @@ class CStereoMatching {
 
  private:
   struct PairResult;
-  bool Rectify(int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf);  // CStereoMatching.cpp:117-168 (staged form)
+  bool Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf, bool& staged_on_device);  // :117-168
   bool RunPair(sb200_ctx* ctx, int CamPair, PairResult& out);
   sb200_ctx* last_ctx_ = nullptr;
 };

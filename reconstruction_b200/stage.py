@@ -90,6 +90,35 @@ def write_dataset(root, pyrm_num, lowest_w, lowest_h, n_pairs=1, isoutput=0, pai
     return root + "config.yml", pairs
 
 
+def write_raw_dataset(root, pyrm_num, lowest_w, lowest_h, origin, cams, images, masks, pairs, isoutput=0):
+    """A data set of ORIGINAL (unrectified) frames in the reference's schema: config.yml, calib_camera.yml and one PNM image
+    + mask per camera.  The host mirror then runs Rectify natively (no staged/ directory).  cams: [(K, Rt)] per camera,
+    images / masks: per camera arrays at `origin` size, pairs: [[camA, camB], ...]."""
+    os.makedirs(os.path.join(root, "mask"), exist_ok=True)
+    root = os.path.join(os.path.abspath(root), "")
+    with open(root + "calib_camera.yml", "w") as f:
+        f.write("%YAML:1.0\n---\n")
+        for i, (k, rt) in enumerate(cams):
+            f.write(_mat(f"intrinsic-{i}", k))
+            f.write(_mat(f"extrinsic-{i}", rt))
+    names = [f"{1:04d}_Cam{i}.ppm" for i in range(len(cams))]
+    for i, n in enumerate(names):
+        img = images[i] if images[i].ndim == 3 else np.repeat(images[i][:, :, None], 3, axis=2)
+        write_pnm(root + n, img)
+        write_pnm(root + "mask/" + n.replace(".ppm", ".pgm"), masks[i])
+    with open(root + "config.yml", "w") as f:
+        f.write("%YAML:1.0\n---\n")
+        f.write(f'filepath: "{root}"\n')
+        f.write(f'outfilename: "{root}out.ply"\n')
+        f.write(f"isoutput: {isoutput}\n")
+        f.write("camera_calib_name: calib_camera.yml\n")
+        f.write(f"PyrmNum: {pyrm_num}\nLowestLevelWidth: {lowest_w}\nLowestLevelHeight: {lowest_h}\n")
+        f.write("imagelist:\n" + "".join(f'   - "{n}"\n' for n in names))
+        f.write("masklist:\n" + "".join(f'   - "mask/{n.replace(".ppm", ".pgm")}"\n' for n in names))
+        f.write(_mat("camID", np.array(pairs), dt="u"))
+    return root + "config.yml"
+
+
 def read_ply_f32(path):
     """(xyz float32 [n,3], bgr uint8 [n,3]) of a cloud written in the reference's PLY layout."""
     with open(path, "rb") as f:

@@ -36,3 +36,31 @@ def test_cli_matches_oracle(oracle, tmp_path):
         all_xyz.append(oxyz.astype(np.float32))
     xyz, _ = stage.read_ply_f32(str(tmp_path / "out.ply"))  # the sink's merged cloud, pair order
     assert np.array_equal(xyz.view(np.int32), np.concatenate(all_xyz).view(np.int32))
+
+
+def test_cli_native_rectify(tmp_path, golden_dir):
+    """`reconstruction config.yml` on ORIGINAL frames: Rectify runs natively (host calibration + device remap/erode); the cloud
+    must equal the one the same C ABI calls produce when driven from Python."""
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    g = np.load(os.path.join(golden_dir, "rectify_cv2.npz"))
+    c = "a"
+    L, (w0, h0) = int(g[c + "_pyrm_num"]), (int(v) for v in g[c + "_lowest"])
+    origin = tuple(int(v) for v in g[c + "_origin"])
+    cams = [(g[c + "_K0"], g[c + "_Rt0"]), (g[c + "_K1"], g[c + "_Rt1"])]
+    cfg = stage.write_raw_dataset(str(tmp_path), L, w0, h0, origin, cams, [g[c + "_src_image0"], g[c + "_src_image1"]],
+                                  [g[c + "_src_mask0"], g[c + "_src_mask1"]], [[0, 1]], isoutput=1)
+    r = subprocess.run([os.path.join(HOST, "reconstruction"), cfg], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    xyz, bgr = stage.read_ply_f32(str(tmp_path / "cloud0.ply"))
+    st = capi.StereoB200(L, w0, h0, *origin)
+    cal = capi.rectify_calib(cams[0][0], cams[0][1], cams[1][0], cams[1][1], origin, w0, L)
+    for j in (0, 1):
+        st.rectify_view(j, g[c + f"_src_image{j}"], g[c + f"_src_mask{j}"], cams[j][0], cal["R_new"][j], cal["P_scaled"][j])
+    st.pair_build()
+    st.set_calib(cal["Q"], cal["R_final"], cal["T_final"])
+    n = st.match_pair()
+    pxyz, pbgr, _ = st.get_points(n)
+    assert len(xyz) == n and n > 0
+    assert np.array_equal(xyz.view(np.int32), pxyz.astype(np.float32).view(np.int32))
+    assert np.array_equal(bgr, pbgr)

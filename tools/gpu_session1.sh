@@ -1,3 +1,3 @@
 set -x
 cd /root/repo
-timeout 900 python -m pytest tests/test_rectify_gpu.py -m gpu -q 2>&1 | tail -25
+timeout 900 python -m pytest tests/test_host_gpu.py -m gpu -q 2>&1 | tail -25
