@@ -157,3 +157,60 @@ def make_pair(
         pyrm_num=pyrm_num,
         lowest_size=(lowest_w, lowest_h),
     )
+
+
+def make_torture_pair(lowest_w: int, lowest_h: int, pyrm_num: int, kind: str, seed: int = 0) -> StagedPair:
+    """Adversarial staged pairs for the parity tests (small sizes, CPU oracle alongside):
+      "flat"   two grey levels only (values 100 / 101, blocks of constant colour): NCC ties and zero-variance windows everywhere
+               (quirk Q10, the screening pass must hand these to the exact search)
+      "holes"  a mask riddled with holes and thin bridges: mode 1 / 2 refinement pixels, hole look-ahead ranges (Q3), wide Rematch ranges
+      "steps"  piecewise-constant disparity with jumps of 6-40 px: refinement pixels leaving their table window, exp() arguments
+               beyond -512, uniqueness / order constraint removals
+      "sat"    heavily saturated texture (large areas clipped to 0 / 255) with fine detail elsewhere
+    """
+    W, H = lowest_w << (pyrm_num - 1), lowest_h << (pyrm_num - 1)
+    rng = np.random.default_rng(777000 + seed)
+    base = make_pair(lowest_w, lowest_h, pyrm_num, pair_id=100 + seed)
+    img0, img1 = base.image[0].copy(), base.image[1].copy()
+    m0, m1 = base.mask[0].copy(), base.mask[1].copy()
+    if kind == "flat":
+        blk = 6
+        g0 = rng.integers(100, 102, (H // blk + 2, W // blk + 40, 3), dtype=np.uint8)
+        canvas = np.repeat(np.repeat(g0, blk, axis=0), blk, axis=1)
+        shift = int(0.08 * W)
+        img0 = np.ascontiguousarray(canvas[:H, shift:shift + W])
+        img1 = np.ascontiguousarray(canvas[:H, :W])  # constant disparity -shift
+        m1 = np.roll(m0, -shift, axis=1)
+        m1[:, -shift - 8:] = 0
+    elif kind == "holes":
+        holes = rng.random((H // 8 + 1, W // 8 + 1)) < 0.22
+        hm = np.repeat(np.repeat(holes, 8, axis=0), 8, axis=1)[:H, :W]
+        thin = (np.arange(W)[None, :] % 37 < 2) | (np.arange(H)[:, None] % 41 < 2)
+        m0[hm | thin] = 0
+        m1[np.roll(hm, -int(0.08 * W), axis=1)] = 0
+    elif kind == "steps":
+        canvas = np.clip(128 + 52 * value_noise(H, W + 200, rng), 0, 255).astype(np.uint8)
+        img0 = np.ascontiguousarray(canvas[:, 100:100 + W])
+        img1 = np.zeros_like(img0)
+        band = H // 6
+        for b, d in enumerate([0, 6, -14, 25, -40, 9, 0]):
+            y0, y1 = b * band, min(H, (b + 1) * band)
+            if y0 >= H:
+                break
+            img1[y0:y1] = canvas[y0:y1, 100 + d:100 + d + W]
+        m1 = m0.copy()
+    elif kind == "sat":
+        t = value_noise(H, W + 64, rng)
+        canvas = np.clip(128 + 400 * t, 0, 255).astype(np.uint8)
+        shift = int(0.05 * W)
+        img0 = np.ascontiguousarray(canvas[:, shift:shift + W])
+        img1 = np.ascontiguousarray(canvas[:, :W])
+        m1 = np.roll(m0, -shift, axis=1)
+        m1[:, -shift - 8:] = 0
+    else:
+        raise ValueError(kind)
+    border = 8
+    for m in (m0, m1):
+        m[:border], m[-border:], m[:, :border], m[:, -border:] = 0, 0, 0, 0
+    return dataclasses.replace(base, image=(np.ascontiguousarray(img0), np.ascontiguousarray(img1)),
+                               mask=(np.ascontiguousarray(m0), np.ascontiguousarray(m1)))

@@ -132,6 +132,42 @@ def test_live_oracle_free_running(lib, oracle, L, w0, h0, pair_id, scale):
     assert g.refine_counters()[1] >= 0
 
 
+@pytest.mark.parametrize("kind,L,w0,h0", [("flat", 2, 96, 72), ("holes", 3, 64, 48), ("steps", 3, 64, 48), ("sat", 2, 120, 90), ("holes", 2, 75, 51)])
+def test_torture_inputs_free_running(lib, oracle, kind, L, w0, h0):
+    """Adversarial inputs (NCC ties and flat windows, holes, disparity jumps, saturation): every dump point of every level,
+    free-running, bit for bit; the screening pass / table misses / generic refinement paths these inputs force are counted."""
+    sp = synth.make_torture_pair(w0, h0, L, kind)
+    o = oracle.CpuStereo("port", L, w0, h0, *sp.origin_size)
+    g = capi.StereoB200(L, w0, h0, *sp.origin_size)
+    for e in (o, g):
+        e.set_pair(*sp.image, *sp.mask)
+        e.set_calib(sp.Q, sp.R_final, sp.T_final)
+    g.refine_counters(reset=True)
+    for lv in range(L):
+        for st in range(1, 11):
+            try:
+                o.run_stage(lv, st)
+            except Exception:  # the reference exit(0)s on a degenerate margin; the ABI reports it
+                with pytest.raises(capi.StereoError):
+                    g.run_stage(lv, st)
+                return
+            g.run_stage(lv, st)
+            if st == 1:
+                assert np.array_equal(o.get_margins(), g.get_margins(lv))
+                continue
+            for d in (0, 1):
+                _check(g.get_disparity(d), o.get_disparity(d, lv), f"{kind}: level {lv} stage {st} ({capi.STAGE_NAMES[st]}) dir {d}")
+    xyz, bgr, pix = g.to_cloud()
+    oxyz = o.to_cloud()
+    assert len(xyz) == len(oxyz)
+    if len(xyz):
+        _check(xyz, oxyz, f"{kind}: points")
+    fallbacks, misses = g.refine_counters()
+    print(f"{kind}: {len(xyz)} points, {fallbacks} pixels left to the exact NCC pass, {misses} out-of-window refinement evaluations")
+    if kind == "flat":
+        assert fallbacks > 0  # ties must not be settled by the screening pass
+
+
 def test_match_pair_one_call(lib, oracle):
     """sb200_match_pair_host (what the C++ mirror calls) == staged run == oracle."""
     L, w0, h0 = 3, 80, 60
