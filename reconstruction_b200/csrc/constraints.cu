@@ -184,23 +184,26 @@ template <class T> __device__ __forceinline__ bool lt2(T a, T b);
 template <> __device__ __forceinline__ bool lt2<short>(short a, short b) { return abs((int)a + (int)b) < 2; }
 template <> __device__ __forceinline__ bool lt2<double>(double a, double b) { return fabs(a + b) < 2; }
 
+// One CTA per row.  Phase 1: the warps compute the (generate, propagate) masks of all 32-pixel chunks of the row in
+// parallel (every load of the row is in flight at once); phase 2: one warp resolves the carry chain chunk by chunk with
+// 64-bit adds; phase 3: the kills are applied.  All tests read the values from BEFORE this pass, which is what the
+// carry formulation needs (a killed p[x-1] and kill(x-1) = 1 give the same outcome).
+#define SB_UNIQUE_MAX_CHUNKS 512  // rows up to 16384 pixels
 template <class T>
-__global__ void __launch_bounds__(128) k_unique(T* __restrict__ P, const T* __restrict__ Qm, int W, long n_px, Bound ms, Bound mt) {
-  const int lane = threadIdx.x & 31;
-  const int y = ms.YL + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (y > ms.YR) return;
+__global__ void __launch_bounds__(256) k_unique(T* __restrict__ P, const T* __restrict__ Qm, int W, long n_px, Bound ms, Bound mt) {
+  __shared__ unsigned s_g[SB_UNIQUE_MAX_CHUNKS], s_p[SB_UNIQUE_MAX_CHUNKS], s_kill[SB_UNIQUE_MAX_CHUNKS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int y = ms.YL + blockIdx.x;
   T* p = P + (size_t)y * W;
-  const T* q = Qm + (size_t)y * W;
   const long row0 = (long)y * W;
   auto qa = [&](int im) -> T {  // flat, clamped to the buffer (memory safety only)
     long f = row0 + im;
     f = f < 0 ? 0 : (f >= n_px ? n_px - 1 : f);
     return Qm[f];
   };
-  (void)q;
-  unsigned cin = 0;
-  for (int base = ms.XL; base <= ms.XR; base += 32) {
-    const int x = base + lane;
+  const int nch = (ms.XR - ms.XL + 32) / 32;
+  for (int c = warp; c < nch; c += nw) {
+    const int x = ms.XL + c * 32 + lane;
     bool g = false, pr = false;
     if (x <= ms.XR) {
       const T pv = p[x];
@@ -217,25 +220,37 @@ __global__ void __launch_bounds__(128) k_unique(T* __restrict__ P, const T* __re
       }
     }
     const unsigned G = __ballot_sync(0xffffffffu, g), Pm = __ballot_sync(0xffffffffu, pr);
-    // adder with generate G, propagate Pm: A = G, B = G | Pm; carry into bit i+1 = kill(i)
-    const unsigned long long A = G, B = (unsigned long long)(G | Pm);
-    const unsigned long long S = A + B + cin;
-    const unsigned long long carries = (S ^ A ^ B) >> 1;  // bit i = carry out of bit i
-    const unsigned kill = (unsigned)carries;
-    if (x <= ms.XR && ((kill >> lane) & 1)) p[x] = (T)SB_NOMATCH;
-    cin = (unsigned)((carries >> 31) & 1);
-    __syncwarp();
+    if (lane == 0) { s_g[c] = G; s_p[c] = Pm; }
+  }
+  __syncthreads();
+  if (warp == 0 && lane == 0) {
+    unsigned cin = 0;
+    for (int c = 0; c < nch; c++) {
+      // adder with generate G, propagate Pm: A = G, B = G | Pm; carry out of bit i = kill(i)
+      const unsigned long long A = s_g[c], B = (unsigned long long)(s_g[c] | s_p[c]);
+      const unsigned long long S = A + B + cin;
+      const unsigned long long carries = (S ^ A ^ B) >> 1;
+      s_kill[c] = (unsigned)carries;
+      cin = (unsigned)((carries >> 31) & 1);
+    }
+  }
+  __syncthreads();
+  for (int c = warp; c < nch; c += nw) {
+    const int x = ms.XL + c * 32 + lane;
+    if (x <= ms.XR && ((s_kill[c] >> lane) & 1)) p[x] = (T)SB_NOMATCH;
   }
 }
 
 int launch_unique_s16(short* P, const short* Qm, int W, int H, Bound ms, Bound mt, cudaStream_t st) {
   if (ms.width <= 0 || ms.height <= 0) return 0;
-  k_unique<short><<<(ms.height + 3) / 4, 128, 0, st>>>(P, Qm, W, (long)W * H, ms, mt);
+  if (ms.width > 32 * SB_UNIQUE_MAX_CHUNKS) return -1;
+  k_unique<short><<<ms.height, 256, 0, st>>>(P, Qm, W, (long)W * H, ms, mt);
   return 1;
 }
 int launch_unique_f64(double* P, const double* Qm, int W, int H, Bound ms, Bound mt, cudaStream_t st) {
   if (ms.width <= 0 || ms.height <= 0) return 0;
-  k_unique<double><<<(ms.height + 3) / 4, 128, 0, st>>>(P, Qm, W, (long)W * H, ms, mt);
+  if (ms.width > 32 * SB_UNIQUE_MAX_CHUNKS) return -1;
+  k_unique<double><<<ms.height, 256, 0, st>>>(P, Qm, W, (long)W * H, ms, mt);
   return 1;
 }
 
