@@ -83,6 +83,7 @@ struct RefineFusedDir {
 struct RefineFusedArgs {
   RefineFusedDir d[2];
   int W, H, T;
+  int use_tma;  // tile load phase through cp.async.bulk.tensor (needs W % 8 == 0), else plain loads
   long n_px;
   double ws;
   unsigned long long* counters;

@@ -168,6 +168,23 @@ def test_torture_inputs_free_running(lib, oracle, kind, L, w0, h0):
         assert fallbacks > 0  # ties must not be settled by the screening pass
 
 
+@pytest.mark.parametrize("iters", [0, 1, 7, 13])
+def test_refine_iteration_override(lib, oracle, iters):
+    """sweep counts that are not a multiple of the sweeps fused per launch (remainder launch), including none at all"""
+    L, w0, h0 = 2, 96, 72
+    sp = synth.make_pair(w0, h0, L, pair_id=8)
+    o = oracle.CpuStereo("port", L, w0, h0)
+    g = capi.StereoB200(L, w0, h0)
+    for e in (o, g):
+        e.set_pair(*sp.image, *sp.mask)
+        e.set_calib(sp.Q, sp.R_final, sp.T_final)
+        e.set_refine_iters(iters)
+        for lv in range(L):
+            e.match_one_layer(lv)
+    for d in (0, 1):
+        _check(g.get_disparity(d), o.get_disparity(d, L - 1), f"{iters} sweeps, dir {d}")
+
+
 def test_match_pair_one_call(lib, oracle):
     """sb200_match_pair_host (what the C++ mirror calls) == staged run == oracle."""
     L, w0, h0 = 3, 80, 60
