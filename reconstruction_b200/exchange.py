@@ -52,6 +52,50 @@ def allgather_points(xyz: torch.Tensor, bgr: torch.Tensor, pix: torch.Tensor, n_
     return cnts, res[0], res[1], res[2]
 
 
+class PointExchanger:
+    """The exchange, overlapped with the next pair's matching (SURVEY.md 8e "Overlap"): `submit` snapshots the local points
+    into a staging buffer on the current stream and starts the all-gathers asynchronously; the matcher may then overwrite
+    its point buffers while NCCL is still sending.  `finish` waits for the gathers of the last submit (the next `submit`
+    does so implicitly before it reuses the staging buffers) and returns the gathered buffers."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.stage = {}
+        self.out = {}
+        self.pending = []
+        self.cnts = None
+
+    def submit(self, xyz, bgr, pix, n_local):
+        self.finish()
+        world = dist.get_world_size(self.group)
+        self.cnts = allgather_counts(n_local, xyz.device, self.group).cpu()
+        nmax = max(int(self.cnts.max()), 1)
+        if xyz.shape[0] < nmax:
+            raise ValueError(f"point buffers hold {xyz.shape[0]} rows but another rank produced {nmax}")
+        for name, t in (("xyz", xyz), ("bgr", bgr), ("pix", pix)):
+            st = self.stage.get(name)
+            if st is None or st.shape[0] < nmax:
+                st = torch.empty((nmax,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                self.stage[name] = st
+            src = st[:nmax]
+            src.copy_(t[:nmax], non_blocking=True)
+            shape = (world,) + tuple(src.shape)
+            buf = self.out.get(name)
+            if buf is None or tuple(buf.shape) != shape:
+                buf = torch.empty(shape, dtype=src.dtype, device=src.device)
+                self.out[name] = buf
+            self.pending.append(dist.all_gather_into_tensor(buf.view(-1), src.reshape(-1), group=self.group, async_op=True))
+        return nmax * world * POINT_BYTES
+
+    def finish(self):
+        for w in self.pending:
+            w.wait()
+        self.pending = []
+        if self.cnts is None:
+            return None
+        return self.cnts, self.out["xyz"], self.out["bgr"], self.out["pix"]
+
+
 def concat_in_pair_order(cnts, xyz_all, bgr_all, pix_all):
     """Flatten the gathered buffers to the reference's InsertPoint order: pair 0's points, then pair 1's, ..."""
     xs, bs, ps = [], [], []

@@ -37,6 +37,16 @@ def _worker(rank, world, port, counts, q):
         for _ in range(2):  # second call reuses the gather buffers
             cnts, xa, ba, pa = exchange.allgather_points(xyz, bgr, pix, n, out=bufs)
         fx, fb, fp = exchange.concat_in_pair_order(cnts, xa, ba, pa)
+        # the overlapped form: submit, clobber the source buffers (as the next pair's matching would), then finish
+        ex = exchange.PointExchanger()
+        for _ in range(2):
+            ex.submit(xyz, bgr, pix, n)
+            keep = (xyz.clone(), bgr.clone(), pix.clone())
+            xyz.fill_(-1.0); bgr.fill_(7); pix.fill_(-5)
+            c2, xa2, ba2, pa2 = ex.finish()
+            xyz.copy_(keep[0]); bgr.copy_(keep[1]); pix.copy_(keep[2])
+        gx, gb, gp = exchange.concat_in_pair_order(c2, xa2, ba2, pa2)
+        assert torch.equal(gx, fx) and torch.equal(gb, fb) and torch.equal(gp, fp) and c2.tolist() == cnts.tolist()
         q.put((rank, cnts.tolist(), fx.numpy().copy(), fb.numpy().copy(), fp.numpy().copy()))
     finally:
         dist.destroy_process_group()
