@@ -47,6 +47,7 @@ struct sb200_ctx {
   int2* istats[2] = {nullptr, nullptr};
   unsigned long long* search_counters = nullptr;  // [2]: [1] = pixels the screening pass left to the exact search
   unsigned* search_list = nullptr;
+  unsigned* search_list2 = nullptr;
   unsigned* search_n = nullptr;
   SearchScratch ss{};
   bool screen = true;                             // SB200_SCREEN=0 disables the integer screening pass
@@ -139,9 +140,9 @@ PairViews make_views(const sb200_ctx* c, int level, bool zeroOne) {
 int ensure_stats(sb200_ctx* c, int level) {
   if (c->stats_level == level) return SB200_OK;
   const Level& l = c->lv[level];
-  // levels whose searches are screened only need the integer map; the exact pass evaluates the few windows it
-  // touches on the spot.  Level 0 (full-range search) and unscreened configurations keep the double map.
-  const bool int_only = c->screen && c->R == 2 && level > 0;
+  // screened searches only need the integer map; the exact pass evaluates the few windows it touches on the spot.
+  // Unscreened configurations (SB200_SCREEN=0, MatchBlockRadius != 2) keep the double map.
+  const bool int_only = c->screen && c->R == 2;
   for (int k = 0; k < 2; k++) {
     const int n = int_only ? launch_window_istats(l.img[k], l.w, l.h, c->istats[k], c->st)
                            : launch_window_stats(l.img[k], l.w, l.h, c->R, c->stats[k], c->R == 2 ? c->istats[k] : nullptr, c->st);
@@ -176,7 +177,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
       if (rc) return rc;
       if (level == 0) {
         for (int d = 0; d < 2; d++) {
-          const int n = launch_lowest_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->ds[d], c->st);
+          const int n = launch_lowest_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, c->st);
           if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
           c->launches += n;
         }
@@ -366,8 +367,9 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   }
   CK(dalloc(&c->search_counters, 2));
   CK(dalloc(&c->search_list, n + pad));
-  CK(dalloc(&c->search_n, 1));
-  c->ss.list = c->search_list; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
+  CK(dalloc(&c->search_list2, n + pad));
+  CK(dalloc(&c->search_n, 2));
+  c->ss.list = c->search_list; c->ss.list2 = c->search_list2; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
   CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
   CK(dalloc(&c->ds_tmp, n + pad));
@@ -419,7 +421,7 @@ void sb200_ctx_destroy(sb200_ctx* c) {
     for (int k = 0; k < 2; k++) { cudaFree(l.img[k]); cudaFree(l.mask[k]); }
   cudaFree(c->d_margins);
   for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); cudaFree(c->istats[d]); }
-  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi); cudaFree(c->search_counters); cudaFree(c->search_list); cudaFree(c->search_n);
+  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi); cudaFree(c->search_counters); cudaFree(c->search_list); cudaFree(c->search_list2); cudaFree(c->search_n);
   for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
   for (int d = 0; d < 2; d++) { cudaFree(c->rs[d].table); cudaFree(c->rs[d].code); cudaFree(c->rs[d].miss_count); cudaFree(c->rs[d].miss_list); }
   cudaFree(c->rs[0].counters);

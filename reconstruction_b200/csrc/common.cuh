@@ -115,6 +115,19 @@ __host__ __device__ inline double sb_exp_twin(double x, const unsigned long long
 // u8 -> f64, exact.
 __device__ __forceinline__ double sb_u2d(unsigned v) { return (double)v; }
 
+// NWORDS 32-bit words starting at byte offset bo of a byte buffer (any alignment): aligned word loads + funnel shifts.
+// Reads up to 4 * (NWORDS + 1) bytes from the aligned address below bo; the image buffers carry slack for that.
+template <int NWORDS>
+__device__ __forceinline__ void load_row_words(const uint8_t* __restrict__ base, long bo, unsigned (&w)[NWORDS]) {
+  const unsigned sh = ((unsigned)bo & 3u) * 8u;
+  const unsigned* __restrict__ p = reinterpret_cast<const unsigned*>(base + (bo & ~3L));  
+  unsigned a[NWORDS + 1];
+#pragma unroll
+  for (int i = 0; i <= NWORDS; i++) a[i] = p[i];
+#pragma unroll
+  for (int i = 0; i < NWORDS; i++) w[i] = __funnelshift_r(a[i], a[i + 1], sh);
+}
+
 // First-max argmax merge used by every NCC search (strict '>' in ascending candidate order,
 // CStereoMatching.cpp:214-218): (v, i) beats (bv, bi) iff v > bv, or v == bv and i < bi.
 __device__ __forceinline__ void sb_argmax_merge(double& bv, int& bi, double v, int i) {

@@ -21,8 +21,9 @@ int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats,
 
 // Scratch of the screened searches (K3, K7): the pixels the integer screening pass could not settle.
 struct SearchScratch {
-  unsigned* list;                // flat pixel indices
-  unsigned* n_list;              // device counter of the current search
+  unsigned* list;                // flat pixel indices left by the per-thread screening pass (or all masked pixels, lowest level)
+  unsigned* list2;               // ... left by the per-warp screening pass: input of the exact pass
+  unsigned* n_list;              // device counters [2] of the current search
   unsigned cap;
   unsigned long long* counters;  // [2]: [1] += n_list after every search (instrumentation)
 };
@@ -30,7 +31,7 @@ struct SearchScratch {
 int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStream_t st);
 
 // K2  LowestLevelInitialMatch (:170-227)
-int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st);
+int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, const SearchScratch* sc, cudaStream_t st);
 // K3  HighLevelInitialMatch (:231-308): prev = refined f64 map of the coarser level (pw x ph)
 int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
                       short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, cudaStream_t st);

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) k_ncc_search(PairViews v, Bound ms, int l
 template <int WS, int G>
 __global__ void __launch_bounds__(256) k_ncc_search_list(PairViews v, const unsigned* __restrict__ list, const unsigned* __restrict__ n_ptr,
                                                          unsigned cap, const short* __restrict__ lo_map,
-                                                         const short* __restrict__ hi_map, short* __restrict__ disp) {
+                                                         const short* __restrict__ hi_map, int lo_const, int hi_const,
+                                                         short* __restrict__ disp) {
   constexpr int R = WS / 2, N = WS * WS * 3, NG = 256 / G;
   __shared__ double s_vec[NG][N];
   const int W = v.W, pitch = 3 * W;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(256) k_ncc_search_list(PairViews v, const unsi
       vec[k] = div_by_common((double)pl[i * pitch + j] - meanL, normL, yl);
     }
     __syncwarp(gmask);
-    const int lo = lo_map[f], hi = hi_map[f];
+    const int lo = lo_map ? (int)lo_map[f] : lo_const, hi = lo_map ? (int)hi_map[f] : hi_const;
     double bv = -1.0;
     int bi = -1;
     for (int im = lo + gl; im <= hi; im += G) {
@@ -173,17 +174,6 @@ __global__ void __launch_bounds__(256) k_ncc_search_list(PairViews v, const unsi
 // ranges (hole look-ahead), windows touching the buffer edge — is appended to a pixel list and evaluated by
 // k_ncc_search_list in the reference's exact arithmetic.
 // ------------------------------------------------------------------------------------------------
-template <int NWORDS>
-__device__ __forceinline__ void load_row_words(const uint8_t* __restrict__ base, long bo, unsigned (&w)[NWORDS]) {
-  const unsigned sh = ((unsigned)bo & 3u) * 8u;
-  const unsigned* __restrict__ p = reinterpret_cast<const unsigned*>(base + (bo & ~3L));  // buffers are cudaMalloc'ed + slack
-  unsigned a[NWORDS + 1];
-#pragma unroll
-  for (int i = 0; i <= NWORDS; i++) a[i] = p[i];
-#pragma unroll
-  for (int i = 0; i < NWORDS; i++) w[i] = __funnelshift_r(a[i], a[i + 1], sh);
-}
-
 template <int MODE>
 __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, const short* __restrict__ lo_map,
                                                      const short* __restrict__ hi_map, short* __restrict__ disp,
@@ -192,11 +182,14 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
   if (x > ms.XR) return;
   const int W = v.W;
   const long f = (long)y * W + x;
-  if (v.mask0[f] != 255) return;
-  if (MODE == SEARCH_REMATCH && disp[f] != SB_NOMATCH) return;
+  // everything that depends only on f is requested together (one memory round trip), tested afterwards
+  const unsigned char m0 = v.mask0[f];
+  const short dv = MODE == SEARCH_REMATCH ? disp[f] : (short)SB_NOMATCH;
   const int lo = lo_map[f], hi = hi_map[f];
-  if (hi < lo) return;  // no candidate: the pixel keeps its value
   const int2 sl = v.istat0[f];
+  if (m0 != 255) return;
+  if (MODE == SEARCH_REMATCH && dv != SB_NOMATCH) return;
+  if (hi < lo) return;  // no candidate: the pixel keeps its value
   const int varL = 75 * sl.y - sl.x * sl.x;
   if (hi - lo > 4 || lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || varL == 0) {
     const unsigned e = atomicAdd(n_list, 1u);
@@ -210,12 +203,22 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
     L[r][3] &= 0x00ffffffu;  // 15 bytes per row
     load_row_words<7>(v.img1, ((long)(y - 2 + r) * W + (lo - 2)) * 3, Rw[r]);
   }
+  // masks and window statistics of all five candidates are requested up front, together with the window rows above, so
+  // the kernel pays two memory round trips per pixel instead of one per candidate (lo + 4 may exceed hi: still inside the
+  // row, see the range test above plus the buffer slack)
+  unsigned char mk[5];
+  int2 st1[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    mk[j] = v.mask1[(long)y * W + lo + j];
+    st1[j] = v.istat1[(long)y * W + lo + j];
+  }
   float best = -3.0e38f, second = -3.0e38f;
   int bj = 0, nvalid = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) {
     const int im = lo + j;
-    const bool valid = im <= hi && v.mask1[(long)y * W + im] == 255;
+    const bool valid = im <= hi && mk[j] == 255;
     const int wi = (3 * j) / 4;
     const unsigned bs = ((3 * j) % 4) * 8;
     unsigned slr = 0;
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
         slr = __dp4a(L[r][i], q, slr);
       }
     if (valid) {
-      const int2 sr = v.istat1[(long)y * W + im];
+      const int2 sr = st1[j];
       const int num = 75 * (int)slr - sl.x * sr.x;
       const int varR = 75 * sr.y - sr.x * sr.x;
       const float fn = (float)num;
@@ -247,6 +250,87 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
   }
 }
 
+// The same screening for ranges of any width (full-range search of the lowest level, hole look-ahead and Rematch ranges):
+// one warp per listed pixel, lanes stride the candidates, (best, second best) merged across the warp.  Settles a pixel
+// under the same margin rule as k_ncc_screen5; the rest goes to `out_list` for the exact pass.
+template <int MODE>
+__global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsigned* __restrict__ list, const unsigned* __restrict__ n_ptr,
+                                                         unsigned cap, const short* __restrict__ lo_map, const short* __restrict__ hi_map,
+                                                         int lo_const, int hi_const, short* __restrict__ disp,
+                                                         unsigned* __restrict__ out_list, unsigned* __restrict__ n_out) {
+  const int W = v.W, lane = threadIdx.x & 31;
+  const unsigned n = min(*n_ptr, cap);
+  const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
+  for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += nwarp) {
+    const long f = list[e];
+    const int y = (int)(f / W), x = (int)(f - (long)y * W);
+    const int lo = lo_map ? (int)lo_map[f] : lo_const, hi = lo_map ? (int)hi_map[f] : hi_const;
+    const int2 sl = v.istat0[f];
+    const int varL = 75 * sl.y - sl.x * sl.x;
+    bool bad = varL == 0 || lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || hi < lo;  // warp-uniform
+    float best = -3.0e38f, second = -3.0e38f;
+    int bi = -1, nvalid = 0;
+    if (!bad) {
+      unsigned L[5][4];
+#pragma unroll
+      for (int r = 0; r < 5; r++) {
+        load_row_words<4>(v.img0, ((long)(y - 2 + r) * W + (x - 2)) * 3, L[r]);
+        L[r][3] &= 0x00ffffffu;
+      }
+      for (int im = lo + lane; im <= hi; im += 32) {
+        const long ft = (long)y * W + im;
+        if (v.mask1[ft] != 255) continue;
+        const int2 sr = v.istat1[ft];
+        unsigned slr = 0;
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+          unsigned q[4];
+          load_row_words<4>(v.img1, ((long)(y - 2 + r) * W + (im - 2)) * 3, q);
+#pragma unroll
+          for (int i = 0; i < 4; i++) slr = __dp4a(L[r][i], q[i], slr);
+        }
+        const int num = 75 * (int)slr - sl.x * sr.x;
+        const int varR = 75 * sr.y - sr.x * sr.x;
+        const float fn = (float)num;
+        const float key = varR == 0 ? 0.0f : fn * fabsf(fn) / (float)varR;
+        nvalid++;
+        if (key > best) { second = best; best = key; bi = im; }
+        else if (key > second) second = key;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
+        const float lo2 = fminf(best, ob);
+        if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+        second = fmaxf(fmaxf(second, os), lo2);
+      }
+    }
+    if (lane == 0) {
+      if (!bad && nvalid == 0) {
+        // no masked candidate in range: the pixel keeps its value (NOMATCH)
+      } else if (!bad && best >= 1.0e-6f * (float)varL && (nvalid == 1 || best - second > 1.0e-4f * best)) {
+        disp[f] = (short)((unsigned short)bi - x);  // ushort temp_i; short(temp_i - x) (:271,:302)
+      } else if (!(bad && hi < lo)) {
+        const unsigned o = atomicAdd(n_out, 1u);
+        if (o < cap) out_list[o] = (unsigned)f;
+      }
+    }
+  }
+}
+
+// list of the masked pixels of the source margin rectangle (input of the full-range search of the lowest level)
+__global__ void __launch_bounds__(256) k_list_masked(const uint8_t* __restrict__ mask0, int W, Bound ms, unsigned* __restrict__ list,
+                                                     unsigned* __restrict__ n_list, unsigned cap) {
+  const int x = ms.XL + blockIdx.x * 256 + threadIdx.x, y = ms.YL + blockIdx.y;
+  if (x > ms.XR) return;
+  const long f = (long)y * W + x;
+  if (mask0[f] != 255) return;
+  const unsigned e = atomicAdd(n_list, 1u);
+  if (e < cap) list[e] = (unsigned)f;
+}
+
 __global__ void k_count_add(const unsigned* __restrict__ n, unsigned long long* __restrict__ total) { *total += *n; }
 
 template <int G, int MODE>
@@ -254,13 +338,18 @@ static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, 
                            short* disp, const SearchScratch* sc, cudaStream_t st) {
   if (ms.width <= 0 || ms.height <= 0) return 0;
   dim3 grid((ms.width + 255) / 256, ms.height);
-  if (R == 2 && MODE != SEARCH_LOWEST && sc) {  // screen first, exact arithmetic for what is left
-    cudaMemsetAsync(sc->n_list, 0, sizeof(unsigned), st);
-    dim3 gs((ms.width + 127) / 128, ms.height);
-    k_ncc_screen5<MODE><<<gs, 128, 0, st>>>(v, ms, lo_map, hi_map, disp, sc->list, sc->n_list, sc->cap);
-    k_ncc_search_list<5, 32><<<148 * 4, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, disp);
-    k_count_add<<<1, 1, 0, st>>>(sc->n_list, sc->counters + 1);
-    return 3;
+  if (R == 2 && sc) {  // screen first (narrow ranges per thread, then any range per warp), exact arithmetic for what is left
+    cudaMemsetAsync(sc->n_list, 0, 2 * sizeof(unsigned), st);
+    if (MODE == SEARCH_LOWEST) {
+      k_list_masked<<<dim3((ms.width + 255) / 256, ms.height), 256, 0, st>>>(v.mask0, v.W, ms, sc->list, sc->n_list, sc->cap);
+    } else {
+      dim3 gs((ms.width + 127) / 128, ms.height);
+      k_ncc_screen5<MODE><<<gs, 128, 0, st>>>(v, ms, lo_map, hi_map, disp, sc->list, sc->n_list, sc->cap);
+    }
+    k_ncc_screen_wide<MODE><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, lo, hi, disp, sc->list2, sc->n_list + 1);
+    k_ncc_search_list<5, 32><<<148 * 4, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, lo, hi, disp);
+    k_count_add<<<1, 1, 0, st>>>(sc->n_list + 1, sc->counters + 1);
+    return 4;
   }
   if (R == 2) k_ncc_search<5, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
   else if (R == 1) k_ncc_search<3, G, MODE><<<grid, 256, 0, st>>>(v, ms, lo, hi, lo_map, hi_map, disp);
@@ -271,9 +360,9 @@ static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, 
 // ------------------------------------------------------------------------------------------------
 // K2  LowestLevelInitialMatch (:170-227): full-range search over [XL1, XR1], one warp per pixel.
 // ------------------------------------------------------------------------------------------------
-int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, cudaStream_t st) {
+int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, const SearchScratch* sc, cudaStream_t st) {
   int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
-  n += search_dispatch<32, SEARCH_LOWEST>(v, ms, R, mt.XL, mt.XR, nullptr, nullptr, out, nullptr, st);
+  n += search_dispatch<32, SEARCH_LOWEST>(v, ms, R, mt.XL, mt.XR, nullptr, nullptr, out, sc, st);
   return n;
 }
 

@@ -133,17 +133,20 @@ __global__ void __launch_bounds__(256) k_window_istats5(const uint8_t* __restric
   if (f >= n_px) return;
   const long first = 2L * W + 2, last = n_px - first;
   if (f < first || f >= last) { istats[f] = make_int2(0, 0); return; }
-  const uint8_t* p0 = img + 3 * (f - first);
-  int S = 0, SS = 0;
+  // 5 rows x 15 bytes as byte-packed words: sum = dp4a(w, 1111), sum of squares = dp4a(w, w)
+  unsigned S = 0, SS = 0;
 #pragma unroll
-  for (int i = 0; i < 5; i++)
+  for (int i = 0; i < 5; i++) {
+    unsigned w[4];
+    load_row_words<4>(img, 3 * (f - first) + (long)i * 3 * W, w);
+    w[3] &= 0x00ffffffu;
 #pragma unroll
-    for (int j = 0; j < 15; j++) {
-      const int b = p0[i * 3 * W + j];
-      S += b;
-      SS += b * b;
+    for (int q = 0; q < 4; q++) {
+      S = __dp4a(w[q], 0x01010101u, S);
+      SS = __dp4a(w[q], w[q], SS);
     }
-  istats[f] = make_int2(S, SS);
+  }
+  istats[f] = make_int2((int)S, (int)SS);
 }
 int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStream_t st) {
   const long n = (long)W * H;
