@@ -242,8 +242,8 @@ def run_ours(args):
 
     def step_e2e(i):
         sp = pairs[i % 2]
-        # exactly the call the C++ CStereoMatching::MatchAllLayer mirror makes: points + colours out, no pixel indices
-        n = g.match_pair_host(*pin_in[i % 2], sp.Q, sp.R_final, sp.T_final, pin_xyz, pin_bgr, None, npx)
+        # exactly the call the C++ CStereoMatching::MatchAllLayer mirror makes (isoutput = 0): the InsertPoint payload (xyz f64) out
+        n = g.match_pair_host(*pin_in[i % 2], sp.Q, sp.R_final, sp.T_final, pin_xyz, None, None, npx)
         exchange(n)
         return n
 
@@ -354,7 +354,7 @@ def run_ours(args):
             "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
             "gpu_launches": tot_launch,
             "e2e": {"value": world * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
-                    "h2d_bytes_per_step": 4 * npx * 2, "d2h_bytes_per_step": int(n_pts_e2e) * 27,
+                    "h2d_bytes_per_step": 4 * npx * 2, "d2h_bytes_per_step": int(n_pts_e2e) * 24,
                     "ms_per_step": e2e_ms / args.steps, "api": "sb200_match_pair_host (pinned host buffers)"},
             "roofline": {"bound": "hbm", "kernel": "k_refine_fused (DisparityRefine: one launch = several Jacobi sweeps of both matching directions, top pyramid level)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,

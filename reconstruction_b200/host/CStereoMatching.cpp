@@ -134,16 +134,18 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
   std::vector<camera>& cur = m_data->cam[CamPair];
   const size_t cap = (size_t)cur[0].image.rows * cur[0].image.cols;
   r.xyz.resize(3 * cap);
-  r.bgr.resize(3 * cap);
+  const bool want_bgr = m_data->isoutput != 0;  // colours are only used by the PLY branch (:754-756); InsertPoint takes xyz
+  if (want_bgr) r.bgr.resize(3 * cap);
+  unsigned char* bgr_out = want_bgr ? r.bgr.data() : nullptr;
   // ConstructPyrm, MatchOneLayer x PyrmNum and DisparityToCloud (CStereoMatching.cpp:21-29) on the device
   int rc;
   if (on_device) {  // frames were rectified in HBM, the pyramid is built: match and fetch the points
     rc = sb200_pair_set_calib(ctx, r.Q.ptr<double>(), r.Rf.ptr<double>(), r.Tf.ptr<double>());
     if (rc == SB200_OK) rc = sb200_match_pair(ctx, &r.n);
-    if (rc == SB200_OK) rc = sb200_get_points(ctx, r.xyz.data(), r.bgr.data(), nullptr);
+    if (rc == SB200_OK) rc = sb200_get_points(ctx, r.xyz.data(), bgr_out, nullptr);
   } else {
     rc = sb200_match_pair_host(ctx, cur[0].image.data, cur[1].image.data, cur[0].mask.data, cur[1].mask.data, r.Q.ptr<double>(),
-                               r.Rf.ptr<double>(), r.Tf.ptr<double>(), r.xyz.data(), r.bgr.data(), nullptr, (int64_t)cap, &r.n);
+                               r.Rf.ptr<double>(), r.Tf.ptr<double>(), r.xyz.data(), bgr_out, nullptr, (int64_t)cap, &r.n);
   }
   if (rc != SB200_OK) {
     r.status = rc;
@@ -151,7 +153,7 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
     return false;
   }
   r.xyz.resize(3 * (size_t)r.n);
-  r.bgr.resize(3 * (size_t)r.n);
+  if (want_bgr) r.bgr.resize(3 * (size_t)r.n);
   for (int k = 0; k < 2; k++) {  // margin[k] of the top level (:27-28)
     sb200_boundary b;
     sb200_get_margin(ctx, m_data->m_PyrmNum - 1, k, &b);
@@ -231,7 +233,7 @@ void CStereoMatching::MatchAllLayer() {
     m_data->cam[p][0].bound = margin[0];
     m_data->cam[p][1].bound = margin[1];
     if (Verbose >= 1) printf("\tconverting disparity to cloud %d... %lld points\n", p, (long long)r.n);
-    if (m_CloudOptimization) m_CloudOptimization->InsertPoints(r.xyz.data(), r.bgr.data(), (size_t)r.n);
+    if (m_CloudOptimization) m_CloudOptimization->InsertPoints(r.xyz.data(), r.bgr.empty() ? nullptr : r.bgr.data(), (size_t)r.n);
     if (m_data->isoutput) {
       char filename[32];
       snprintf(filename, sizeof filename, "cloud%d.ply", p);
