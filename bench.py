@@ -38,6 +38,7 @@ METRIC = "disparity Mpix/s (and 3D pts/s) at 10-view 4096x3072, 1/2/4/8 GPU vs C
 CONFIGS = {  # name -> (pyrm_num, lowest_w, lowest_h, description)
     "C": (5, 256, 192, "10-view 4096x3072 synthetic rig, 5-level pyramid (BASELINE.json configs[2]); one adjacent pair per GPU per step"),
     "B": (3, 512, 384, "10-view 2048x1536 synthetic rig, 3-level pyramid (BASELINE.json configs[1]); one adjacent pair per GPU per step"),
+    "E": (5, 375, 250, "20-view 6000x4000 synthetic rig, 5-level pyramid (BASELINE.json configs[4] frame size); one adjacent pair per GPU per step"),
     "small": (3, 128, 96, "512x384 3-level smoke configuration"),
 }
 ALGO_BYTES_PER_PX_ITER = 22  # f64 in 8 + f64 out 8 + BGR 3 + 3
