@@ -180,7 +180,7 @@ class _DevArr:
 
 
 def run_ours(args):
-    import numpy as np
+    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -203,49 +203,60 @@ def run_ours(args):
     L, w0, h0, desc = CONFIGS[args.config]
     W, H = w0 << (L - 1), h0 << (L - 1)
     npx = W * H
+    NC = max(1, args.pairs_in_flight)  # camera pairs in flight per GPU: one context + one stream + one host thread each
     t0 = time.time()
     pairs = [synth.make_pair(w0, h0, L, pair_id=2 * rank + k) for k in range(2)]  # two inputs, alternated between steps
     log(f"[rank {rank}] synthetic pairs {W}x{H} built in {time.time() - t0:.1f}s")
-    g = capi.StereoB200(L, w0, h0, device=local)
-    stream = torch.cuda.ExternalStream(g.stream(), device=local)
+    gs = [capi.StereoB200(L, w0, h0, device=local) for _ in range(NC)]
+    streams = [torch.cuda.ExternalStream(g.stream(), device=local) for g in gs]
 
-    # device-resident inputs (for `value`) and pinned host inputs / outputs (for `e2e`)
+    # device-resident inputs (for `value`) and pinned host inputs / outputs (for `e2e`); inputs are read-only and shared
     dev_in, pin_in = [], []
     for sp in pairs:
         host = [torch.from_numpy(a) for a in (*sp.image, *sp.mask)]
         pin_in.append([h.pin_memory() for h in host])
         dev_in.append([h.cuda(local) for h in host])
-    pin_xyz = torch.empty((npx, 3), dtype=torch.float64).pin_memory()
-    pin_bgr = torch.empty((npx, 3), dtype=torch.uint8).pin_memory()
-    pin_pix = torch.empty(npx, dtype=torch.int32).pin_memory()
+    pin_xyz = [torch.empty((npx, 3), dtype=torch.float64).pin_memory() for _ in range(NC)]
     torch.cuda.synchronize()
 
-    exchanger = xchg.PointExchanger() if world > 1 else None
+    exchangers = [xchg.PointExchanger() for _ in range(NC)] if world > 1 else None
+    # NCCL collectives must be issued in the same order on every rank: the contexts of a rank take turns
+    # (step 0 ctx 0, step 0 ctx 1, step 1 ctx 0, ...) through this ticket
+    turn = threading.Condition()
+    ticket = [0]
+    aborted = []
 
-    def exchange(n_local):
+    def exchange(k, seq, n_local):
         """All-gather of the per-pair point buffers over NCCL, overlapped with the next pair's matching
-        (reconstruction_b200/exchange.py::PointExchanger); the last one is waited for inside the timed region."""
-        if world == 1:
-            return 0
-        xp, bp, pp, _ = g.points_device()
-        xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
-        bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
-        pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
-        return exchanger.submit(xyz, bgr, pix, n_local)
+        (reconstruction_b200/exchange.py::PointExchanger); the last ones are waited for inside the timed region."""
+        if world == 1 or exchangers is None:
+            return
+        with turn:
+            while ticket[0] != seq * NC + k:
+                if aborted:
+                    raise RuntimeError("another context of this rank failed")
+                turn.wait(timeout=1.0)
+            xp, bp, pp, _ = gs[k].points_device()
+            xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
+            bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
+            pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
+            exchangers[k].submit(xyz, bgr, pix, n_local)
+            ticket[0] += 1
+            turn.notify_all()
 
-    def step_resident(i):
-        sp = pairs[i % 2]
-        g.set_calib(sp.Q, sp.R_final, sp.T_final)
-        g.stage_device(*dev_in[i % 2])
-        n = g.match_pair()
-        exchange(n)
+    def step_resident(k, i):
+        sp = pairs[(i + k) % 2]
+        gs[k].set_calib(sp.Q, sp.R_final, sp.T_final)
+        gs[k].stage_device(*dev_in[(i + k) % 2])
+        n = gs[k].match_pair()
+        exchange(k, i, n)
         return n
 
-    def step_e2e(i):
-        sp = pairs[i % 2]
+    def step_e2e(k, i):
+        sp = pairs[(i + k) % 2]
         # exactly the call the C++ CStereoMatching::MatchAllLayer mirror makes (isoutput = 0): the InsertPoint payload (xyz f64) out
-        n = g.match_pair_host(*pin_in[i % 2], sp.Q, sp.R_final, sp.T_final, pin_xyz, None, None, npx)
-        exchange(n)
+        n = gs[k].match_pair_host(*pin_in[(i + k) % 2], sp.Q, sp.R_final, sp.T_final, pin_xyz[k], None, None, npx)
+        exchange(k, i, n)
         return n
 
     def barrier():
@@ -253,38 +264,82 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, profile=False):
+    def timed(step_fn, steps, ctxs, profile=False):
+        """`steps` steps on every context in `ctxs` (one host thread per context when there are several), device time from the
+        first enqueue to the completion of every context's last step, max over ranks."""
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g.set_profiling(profile)
-        if profile:
-            g.stage_ms(reset=True)
-            g.refine_profile(reset=True)
-        launches0 = g.launch_count()
+        for k in ctxs:
+            gs[k].set_profiling(profile)
+            if profile:
+                gs[k].stage_ms(reset=True)
+                gs[k].refine_profile(reset=True)
+        launches0 = sum(gs[k].launch_count() for k in ctxs)
+        ticket[0] = 0
+        npts = [0] * NC
+        errs = []
+
+        def work(k):
+            try:
+                with torch.cuda.stream(streams[k]):
+                    for i in range(steps):
+                        npts[k] = step_fn(k, i)
+            except BaseException as e:  # noqa: BLE001
+                errs.append(e)
+                aborted.append(k)
+                with turn:
+                    turn.notify_all()
+
         barrier()
-        n = 0
-        with torch.cuda.stream(stream):
-            ev0.record(stream)
-            for i in range(steps):
-                n = step_fn(i)
-            if exchanger is not None:
-                exchanger.finish()  # the last step's gathers complete inside the timed region
-            ev1.record(stream)
+        lead = streams[ctxs[0]]
+        ev0.record(lead)  # the device is idle here (barrier above), so this is the start of every context's work
+        if len(ctxs) == 1:
+            work(ctxs[0])
+        else:
+            th = [threading.Thread(target=work, args=(k,)) for k in ctxs]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+        if errs:
+            raise errs[0]
+        with torch.cuda.stream(lead):
+            if exchangers is not None:
+                for k in ctxs:
+                    exchangers[k].finish()  # the last steps' gathers complete inside the timed region
+            for k in ctxs[1:]:
+                lead.wait_stream(streams[k])
+            ev1.record(lead)
         barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, n, g.launch_count() - launches0
+        return ms, npts[ctxs[0]], sum(gs[k].launch_count() for k in ctxs) - launches0
 
-    with torch.cuda.stream(stream):
-        for i in range(args.warmup):
-            step_resident(i)
+    every = list(range(NC))
+    for k in every:
+        with torch.cuda.stream(streams[k]):
+            for i in range(args.warmup):
+                gs[k].set_calib(pairs[i % 2].Q, pairs[i % 2].R_final, pairs[i % 2].T_final)
+                gs[k].stage_device(*dev_in[i % 2])
+                gs[k].match_pair()
+
+    # (1) one pair at a time on context 0, with the per-stage / per-launch timers on: the roofline and stage figures
+    g = gs[0]
+    saved_world_exchange = exchangers
+    single_ms, n_pts, single_launches = None, 0, 0
+    if NC > 1:
+        exchangers = None  # the single-context pass times the matcher alone
+        single_ms, n_pts, single_launches = timed(step_resident, args.steps, [0], profile=True)
+        exchangers = saved_world_exchange
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms, n_pts, launches = timed(step_resident, args.steps, profile=True)
+    # (2) the headline: NC pairs in flight per GPU
+    ms, n_pts2, launches = timed(step_resident, args.steps, every, profile=(NC == 1))
     clocks = sampler.stop() if rank == 0 else None
+    n_pts = n_pts or n_pts2
     stage_ms = g.stage_ms(reset=True)
     ncc_ms = g.stage_level_ms(2, L - 1)  # HighLevelInitialMatch at the top level, both directions
     ncc_px = int(sum(int(m[4]) * int(m[5]) for m in g.get_margins(L - 1)))
@@ -293,10 +348,11 @@ def run_ours(args):
     all_ms, all_n, all_px = g.refine_profile(level=-1, reset=True)
     g.set_profiling(False)
 
-    with torch.cuda.stream(stream):
-        for i in range(min(args.warmup, 2)):
-            step_e2e(i)
-    e2e_ms, n_pts_e2e, _ = timed(step_e2e, args.steps)
+    for k in every:
+        with torch.cuda.stream(streams[k]):
+            for i in range(min(args.warmup, 2)):
+                gs[k].match_pair_host(*pin_in[i % 2], pairs[i % 2].Q, pairs[i % 2].R_final, pairs[i % 2].T_final, pin_xyz[k], None, None, npx)
+    e2e_ms, n_pts_e2e, _ = timed(step_e2e, args.steps, every)
 
     # Rectify (the step before the hot path), measured once per run, outside the timed steps: host calibration +
     # H2D of the two original frames + device maps / remap / erode + pyramid
@@ -324,10 +380,10 @@ def run_ours(args):
                    "(H2D 100.7 MB inside), best of 3", "Mpix_per_s": 2 * npx / (min(ts) * 1e-3) / 1e6}
 
     # totals over ranks
-    tot_pts = n_pts
+    tot_pts = n_pts * NC
     tot_launch = launches
     if world > 1:
-        t = torch.tensor([n_pts, launches], dtype=torch.int64, device="cuda")
+        t = torch.tensor([n_pts * NC, launches], dtype=torch.int64, device="cuda")
         dist.all_reduce(t)
         tot_pts, tot_launch = int(t[0].item()), int(t[1].item())
 
@@ -345,18 +401,29 @@ def run_ours(args):
         achieved = ALGO_BYTES_PER_PX_ITER * top_px / (top_ms * 1e-3) / 1e9 if top_ms > 0 else None
         achieved_all = ALGO_BYTES_PER_PX_ITER * all_px / (all_ms * 1e-3) / 1e9 if all_ms > 0 else None
         sec = ms * 1e-3
+        prof_steps = args.steps  # steps the profiled pass ran on context 0
         out = {
-            "metric": METRIC, "value": world * npx * args.steps / sec / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "metric": METRIC, "value": world * NC * npx * args.steps / sec / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "pairs_per_gpu_per_step": 1, "top_size": [W, H], "pyrm_num": L,
-                       "l2": "inputs larger than L2: ~2.4 GB working set per step, two alternating input pairs",
+            "config": {"workload": desc.replace("one adjacent pair per GPU per step", f"{NC} adjacent pair(s) per GPU per step"),
+                       "pairs_per_gpu_per_step": NC,
+                       "pairs_in_flight": f"{NC} contexts per GPU (one stream and one host thread each): a step matches {NC} camera pairs "
+                                          "concurrently, as the C++ CStereoMatching mirror does (SB200_CTX_PER_DEVICE)",
+                       "top_size": [W, H], "pyrm_num": L,
+                       "l2": f"inputs larger than L2: ~{2.4 * NC:.1f} GB working set per step, two alternating input pairs",
                        "exchange": "all-gather of point buffers over NCCL, overlapped with the next pair's matching" if world > 1 else "none (1 GPU)"},
             "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
             "gpu_launches": tot_launch,
-            "e2e": {"value": world * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
-                    "h2d_bytes_per_step": 4 * npx * 2, "d2h_bytes_per_step": int(n_pts_e2e) * 24,
-                    "ms_per_step": e2e_ms / args.steps, "api": "sb200_match_pair_host (pinned host buffers)"},
+            "e2e": {"value": world * NC * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
+                    "h2d_bytes_per_step": 4 * npx * 2 * NC, "d2h_bytes_per_step": int(n_pts_e2e) * 24 * NC,
+                    "ms_per_step": e2e_ms / args.steps, "api": "sb200_match_pair_host (pinned host buffers), one call per pair and context"},
+            "one_pair_at_a_time": None if single_ms is None else {
+                "value": world * npx * args.steps / (single_ms * 1e-3) / 1e6, "unit": "Mpix/s", "ms_per_pair": single_ms / args.steps,
+                "gpu_launches": single_launches,
+                "what": "the same steps on one context (one pair in flight per GPU), timed the same way just before the headline region; "
+                        "roofline, ncc_top_level and stage_ms_per_step are taken from this pass so that another pair's kernels do not "
+                        "sit between the timing events"},
             "roofline": {"bound": "hbm", "kernel": "k_refine_fused (DisparityRefine: one launch = several Jacobi sweeps of both matching directions, top pyramid level)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
@@ -366,12 +433,12 @@ def run_ours(args):
                                         "launches_timed": all_n}},
             # the NCC cost-volume stage the north star names (HighLevelInitialMatch, top level, both directions: integer
             # statistics + ranges + dp4a screening + exact FP64 pass): 12 algorithmic B per source-margin pixel
-            "ncc_top_level": {"ms_per_step": ncc_ms / args.steps, "pixels": ncc_px,
-                              "achieved_GBps": (12 * ncc_px * args.steps / (ncc_ms * 1e-3) / 1e9) if ncc_ms > 0 else None,
-                              "frac_of_hbm_peak": (12 * ncc_px * args.steps / (ncc_ms * 1e-3) / 1e9 / peak) if ncc_ms > 0 else None,
-                              "exact_fallback_pixels_per_step": int(counters[0]) // max(args.steps, 1)},
+            "ncc_top_level": {"ms_per_step": ncc_ms / prof_steps, "pixels": ncc_px,
+                              "achieved_GBps": (12 * ncc_px * prof_steps / (ncc_ms * 1e-3) / 1e9) if ncc_ms > 0 else None,
+                              "frac_of_hbm_peak": (12 * ncc_px * prof_steps / (ncc_ms * 1e-3) / 1e9 / peak) if ncc_ms > 0 else None,
+                              "exact_fallback_pixels_per_step": int(counters[0]) // max(prof_steps, 1)},
             "rectify": rectify,
-            "stage_ms_per_step": {k: round(float(stage_ms[i]) / args.steps, 4) for i, k in enumerate(
+            "stage_ms_per_step": {k: round(float(stage_ms[i]) / prof_steps, 4) for i, k in enumerate(
                 ["pyramid", "FindMargin", "InitialMatch", "Smooth", "Order", "Unique1", "Rematch", "Unique2", "Median", "Refine",
                  "Unique3", "ToCloud", "RefineSweepsOnly"])},
             "clocks": clocks,
@@ -398,6 +465,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="C")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--pairs-in-flight", type=int, default=3, help="camera pairs matched concurrently per GPU (contexts per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

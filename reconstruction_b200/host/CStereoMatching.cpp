@@ -179,8 +179,12 @@ void CStereoMatching::MatchAllLayer() {
   }
   const int P = m_data->m_CampairNum;
   const int L = m_data->m_PyrmNum;
-  // contexts: one per device; without an explicit list, add devices until creation fails
+  // contexts: first one per device (without an explicit list, add devices until creation fails), then further contexts
+  // round-robin over those devices up to `contexts_per_device` each: every context is one camera pair in flight (own
+  // stream, own host thread), so a device overlaps one pair's latency-bound coarse levels and host<->device copies with
+  // another pair's top-level sweeps.  Pairs are independent (:17), so the results do not depend on the split.
   std::vector<sb200_ctx*> ctxs;
+  std::vector<int> ctx_dev;
   for (int i = 0; devs.empty() ? (i < 64 && (int)ctxs.size() < P) : (i < (int)devs.size()); i++) {
     sb200_ctx* c = nullptr;
     const int dev = devs.empty() ? i : devs[i];
@@ -196,6 +200,25 @@ void CStereoMatching::MatchAllLayer() {
       return;
     }
     ctxs.push_back(c);
+    ctx_dev.push_back(dev);
+  }
+  const int n_dev = (int)ctxs.size();
+  int per_dev = contexts_per_device;
+  if (per_dev <= 0) {
+    const char* e = getenv("SB200_CTX_PER_DEVICE");
+    per_dev = e ? atoi(e) : 3;
+  }
+  if (per_dev < 1) per_dev = 1;
+  for (int j = n_dev; j < n_dev * per_dev && j < P; j++) {
+    sb200_ctx* c = nullptr;
+    const int dev = ctx_dev[j % n_dev];
+    if (sb200_ctx_create(&c, dev, L, m_data->m_LowestLevelSize.width, m_data->m_LowestLevelSize.height, m_data->m_OriginSize.width,
+                         m_data->m_OriginSize.height, MatchBlockRadius, m_ws, m_offset) != SB200_OK) {
+      if (c) sb200_ctx_destroy(c);
+      break;  // not enough memory for another pair in flight: carry on with what there is
+    }
+    ctxs.push_back(c);
+    ctx_dev.push_back(dev);
   }
   const int G = (int)ctxs.size();
   std::vector<PairResult> results(P);
@@ -205,13 +228,13 @@ void CStereoMatching::MatchAllLayer() {
       printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
       RunPair(ctxs[0], p, results[p]);
     }
-  } else {  // pair p -> device p mod G; each worker owns its context
+  } else {  // pair p -> context p mod G, context j on device j mod n_dev; each worker owns its context
     std::mutex io;
     std::vector<std::thread> workers;
     for (int g = 0; g < G; g++)
       workers.emplace_back([&, g]() {
         for (int p = g; p < P; p += G) {
-          { std::lock_guard<std::mutex> lk(io); printf("processing pair %d on GPU %d: cam %d and cam %d...\n", p + 1, g, m_data->cam[p][0].camID, m_data->cam[p][1].camID); }
+          { std::lock_guard<std::mutex> lk(io); printf("processing pair %d on GPU %d: cam %d and cam %d...\n", p + 1, ctx_dev[g], m_data->cam[p][0].camID, m_data->cam[p][1].camID); }
           RunPair(ctxs[g], p, results[p]);
         }
       });

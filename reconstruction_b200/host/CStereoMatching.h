@@ -1,7 +1,7 @@
 // CStereoMatching.h — host mirror of the reference's matcher class (reconstruction/CStereoMatching.h:35-69): same
 // public members and methods; the per-pair body of MatchAllLayer runs on the GPU through the C ABI
-// (include/stereo_b200.h).  One context per GPU; with several GPUs the camera pairs are dealt round-robin to one
-// worker thread per device and handed to the sink in pair order.
+// (include/stereo_b200.h).  `contexts_per_device` contexts per GPU (camera pairs in flight: one stream and one worker
+// thread each); the camera pairs are dealt round-robin to the workers and handed to the sink in pair order.
 #pragma once
 #include <string>
 #include <vector>
@@ -29,6 +29,7 @@ class CStereoMatching {
 
   // --- additions of the mirror (not in the reference) ---
   std::vector<int> devices;        // CUDA devices to use; empty = SB200_DEVICES or every visible device
+  int contexts_per_device = 0;     // camera pairs in flight per device; <= 0 = SB200_CTX_PER_DEVICE or 3
   int last_status = 0;             // sb200 status of the last failing call, 0 if none
   std::string last_error;
   double gpu_seconds = 0;          // wall time spent inside the C ABI (all pairs)
