@@ -89,7 +89,7 @@ bool CManageData::Init(sbcv::FileStorage fs) {
     m_OriginSize = sbcv::Size(ow, oh);
   } else {
     sbcv::Mat img;
-    if (masklist.empty() || !sbcv::imread_pnm(m_FilePath + masklist[0], img, true)) {
+    if (masklist.empty() || !sbcv::imread(m_FilePath + masklist[0], img, true)) {
       printf("cannot read %s to determine the original size\n", masklist.empty() ? "masklist[0]" : masklist[0].c_str());
       return false;
     }

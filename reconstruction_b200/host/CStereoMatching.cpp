@@ -53,11 +53,11 @@ bool CStereoMatching::Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Qo, sbcv::
   if (!fs.isOpened()) {  // ---- (1) native ----
     sbcv::Mat src[2], msk[2];
     for (int j = 0; j < 2; j++) {
-      if (!sbcv::imread_pnm(cur[j].image_name, src[j], false)) {
+      if (!sbcv::imread(cur[j].image_name, src[j], false)) {
         printf("read image %s error\n", cur[j].image_name.c_str());  // :147-151
         return false;
       }
-      if (!sbcv::imread_pnm(cur[j].mask_name, msk[j], true) || msk[j].cols != src[j].cols || msk[j].rows != src[j].rows) {
+      if (!sbcv::imread(cur[j].mask_name, msk[j], true) || msk[j].cols != src[j].cols || msk[j].rows != src[j].rows) {
         printf("read image %s error\n", cur[j].mask_name.c_str());
         return false;
       }

@@ -1,9 +1,12 @@
 // reconstruction <config.yml>   — CLI of the reference (reconstruction/main.cpp:5-24) on the B200 path.
 //   --dump-config <config.yml>   parse only (no GPU): print what CManageData::Init read, as JSON
+//   --decode <in> <out.pnm> [gray]   decode one image file with the native readers (no GPU) and write it as PNM
+//   --dump-yaml <file.yml>       parse only: print every node the OpenCV-YAML reader found, as JSON
 #include <stdio.h>
 #include <string.h>
 
 #include <chrono>
+#include <string>
 
 #include "CReconstruction.h"
 
@@ -28,6 +31,47 @@ static void dump(const CManageData& d) {
   printf("]}\n");
 }
 
+static void json_string(const std::string& s) {
+  putchar('"');
+  for (unsigned char ch : s) {
+    if (ch == '"' || ch == '\\') printf("\\%c", ch);
+    else if (ch < 0x20) printf("\\u%04x", ch);
+    else putchar(ch);
+  }
+  putchar('"');
+}
+
+static void dump_node(const sbcv::FileNode& n) {
+  switch (n.kind) {
+    case sbcv::FileNode::SCALAR: json_string(n.scalar); break;
+    case sbcv::FileNode::SEQ:
+      printf("[");
+      for (size_t i = 0; i < n.seq.size(); i++) { if (i) printf(", "); json_string(n.seq[i]); }
+      printf("]");
+      break;
+    case sbcv::FileNode::MATRIX:
+      printf("{\"rows\": %d, \"cols\": %d, \"channels\": %d, \"dt\": \"%s\", \"hex\": [", n.rows, n.cols, n.channels, n.dt.c_str());
+      for (size_t i = 0; i < n.values.size(); i++) {  // exact: the IEEE bits of every element
+        unsigned long long u;
+        memcpy(&u, &n.values[i], 8);
+        printf("%s\"%016llx\"", i ? ", " : "", u);
+      }
+      printf("]}");
+      break;
+    case sbcv::FileNode::MAP:
+      printf("{");
+      for (size_t i = 0; i < n.child_keys.size(); i++) {
+        if (i) printf(", ");
+        json_string(n.child_keys[i]);
+        printf(": ");
+        dump_node(n.child_nodes[i]);
+      }
+      printf("}");
+      break;
+    default: printf("null");
+  }
+}
+
 int main(int Argc, char** Argv) {
   const auto start = std::chrono::steady_clock::now();
   auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count(); };
@@ -35,6 +79,32 @@ int main(int Argc, char** Argv) {
   if (Argc <= 1) {
     printf("USAGE: reconstruction your_config_file.yml\n");
     return -1;
+  }
+  if (Argc >= 4 && strcmp(Argv[1], "--decode") == 0) {
+    sbcv::Mat img;
+    if (!sbcv::imread(Argv[2], img, Argc >= 5 && strcmp(Argv[4], "gray") == 0)) {
+      printf("read image %s error: %s\n", Argv[2], sbcv::imread_error().c_str());
+      return 1;
+    }
+    return sbcv::imwrite_pnm(Argv[3], img) ? 0 : 1;
+  }
+  if (Argc >= 3 && strcmp(Argv[1], "--dump-yaml") == 0) {
+    sbcv::FileStorage fs(Argv[2], sbcv::FileStorage::READ);
+    if (!fs.isOpened()) {
+      printf("cannot open file %s: %s\n", Argv[2], fs.error().c_str());
+      return 1;
+    }
+    printf("{");
+    bool first = true;
+    for (const std::string& k : fs.keys()) {
+      if (!first) printf(", ");
+      first = false;
+      json_string(k);
+      printf(": ");
+      dump_node(fs[k]);
+    }
+    printf("}\n");
+    return 0;
   }
   if (Argc >= 3 && strcmp(Argv[1], "--dump-config") == 0) {
     if (recon.Init(Argv[2]) == false) return -1;

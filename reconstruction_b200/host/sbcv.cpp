@@ -1,6 +1,7 @@
 #include "sbcv.h"
 
 #include <ctype.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -78,92 +79,152 @@ static int indent_of(const std::string& l) {
   return n;
 }
 
-bool FileStorage::open(const std::string& path) {
-  opened_ = false;
-  nodes_.clear();
-  std::ifstream in(path.c_str());
-  if (!in) { err_ = "cannot open " + path; return false; }
+static double yaml_number(const std::string& t) {
+  const std::string s = trim(t);
+  const char* c = s.c_str();
+  const bool neg = *c == '-';
+  if (*c == '-' || *c == '+') c++;
+  if (*c == '.' && (c[1] == 'I' || c[1] == 'i')) return neg ? -HUGE_VAL : HUGE_VAL;  // .Inf
+  if (*c == '.' && (c[1] == 'N' || c[1] == 'n')) return NAN;                             // .Nan
+  return strtod(s.c_str(), nullptr);
+}
+
+namespace {
+struct YamlParser {
   std::vector<std::string> lines;
-  for (std::string l; std::getline(in, l);) {
-    if (!l.empty() && l.back() == '\r') l.pop_back();
-    lines.push_back(l);
-  }
-  size_t i = 0;
-  auto blank = [&](const std::string& l) { const std::string t = trim(l); return t.empty() || t[0] == '#'; };
+  std::string err;
+  static bool blank(const std::string& l) { const std::string t = trim(l); return t.empty() || t[0] == '#'; }
   // gathers "[ ... ]" possibly spread over several lines, starting with `first` (text after the key)
-  auto gather_flow = [&](std::string first, size_t& idx) {
+  std::string gather_flow(const std::string& first, size_t& idx) const {
     std::string body = first;
     while (body.find(']') == std::string::npos && idx < lines.size()) body += " " + trim(lines[idx++]);
     const size_t a = body.find('['), b = body.rfind(']');
     return (a == std::string::npos || b == std::string::npos || b < a) ? std::string() : body.substr(a + 1, b - a - 1);
-  };
-  while (i < lines.size()) {
-    const std::string& l = lines[i];
-    if (blank(l) || l[0] == '%' || trim(l) == "---" || trim(l) == "...") { i++; continue; }
-    if (indent_of(l) != 0) { i++; continue; }  // stray continuation
-    const size_t colon = l.find(':');
-    if (colon == std::string::npos) { i++; continue; }
-    const std::string key = trim(l.substr(0, colon));
-    std::string rest = trim(l.substr(colon + 1));
-    i++;
-    FileNode n;
-    if (rest.compare(0, 15, "!!opencv-matrix") == 0) {
-      n.kind = FileNode::MATRIX;
-      while (i < lines.size() && (blank(lines[i]) || indent_of(lines[i]) > 0)) {
-        if (blank(lines[i])) { i++; continue; }
-        const std::string t = trim(lines[i]);
-        const size_t c2 = t.find(':');
-        i++;
-        if (c2 == std::string::npos) continue;
-        const std::string k2 = trim(t.substr(0, c2)), v2 = trim(t.substr(c2 + 1));
-        if (k2 == "rows") n.rows = atoi(v2.c_str());
-        else if (k2 == "cols") n.cols = atoi(v2.c_str());
-        else if (k2 == "dt") n.dt = unquote(v2);
-        else if (k2 == "data") {
-          for (const std::string& s : split_flow(gather_flow(v2, i))) n.values.push_back(strtod(s.c_str(), nullptr));
-        }
-      }
-      if ((size_t)n.rows * n.cols != n.values.size() && !n.values.empty() && n.rows > 0 && n.cols > 0 &&
-          n.values.size() % ((size_t)n.rows * n.cols) != 0) {
-        err_ = "matrix " + key + ": rows*cols does not match data";
-        return false;
-      }
-    } else if (!rest.empty() && rest[0] == '[') {
-      n.kind = FileNode::SEQ;
-      n.seq = split_flow(gather_flow(rest, i));
-    } else if (rest.empty()) {
-      n.kind = FileNode::SEQ;
-      while (i < lines.size() && (blank(lines[i]) || indent_of(lines[i]) > 0 || trim(lines[i])[0] == '-')) {
-        if (blank(lines[i])) { i++; continue; }
-        std::string t = trim(lines[i]);
-        if (t[0] != '-') break;
-        i++;
-        n.seq.push_back(unquote(t.substr(1)));
-      }
-    } else {
-      n.kind = FileNode::SCALAR;
-      n.scalar = unquote(rest);
-    }
-    nodes_[key] = n;
   }
+  // first ':' that ends a key: outside quotes and followed by a blank or the end of the line
+  static size_t key_colon(const std::string& l) {
+    char q = 0;
+    for (size_t k = 0; k < l.size(); k++) {
+      const char ch = l[k];
+      if (q) { if (ch == q) q = 0; continue; }
+      if (ch == '"' || ch == '\'') { q = ch; continue; }
+      if (ch == ':' && (k + 1 == l.size() || l[k + 1] == ' ' || l[k + 1] == '\t')) return k;
+    }
+    return std::string::npos;
+  }
+  size_t next_content(size_t i) const {
+    while (i < lines.size() && blank(lines[i])) i++;
+    return i;
+  }
+  // mapping whose keys sit at column `indent`; stops at the first line indented less
+  bool parse_map(size_t& i, int indent, FileNode& out) {
+    out.kind = FileNode::MAP;
+    while (i < lines.size()) {
+      const std::string& l = lines[i];
+      const std::string t = trim(l);
+      if (blank(l) || (indent == 0 && (l[0] == '%' || t == "---" || t == "..."))) { i++; continue; }
+      const int ind = indent_of(l);
+      if (ind < indent) return true;
+      if (ind > indent) { i++; continue; }  // stray continuation
+      const size_t colon = key_colon(l);
+      if (colon == std::string::npos) { i++; continue; }
+      const std::string key = unquote(l.substr(0, colon));
+      const std::string rest = trim(l.substr(colon + 1));
+      i++;
+      FileNode n;
+      if (rest.compare(0, 15, "!!opencv-matrix") == 0) {
+        n.kind = FileNode::MATRIX;
+        while (i < lines.size() && (blank(lines[i]) || indent_of(lines[i]) > indent)) {
+          if (blank(lines[i])) { i++; continue; }
+          const std::string m = trim(lines[i]);
+          const size_t c2 = m.find(':');
+          i++;
+          if (c2 == std::string::npos) continue;
+          const std::string k2 = trim(m.substr(0, c2)), v2 = trim(m.substr(c2 + 1));
+          if (k2 == "rows") n.rows = atoi(v2.c_str());
+          else if (k2 == "cols") n.cols = atoi(v2.c_str());
+          else if (k2 == "dt") {
+            n.dt = unquote(v2);
+            n.channels = isdigit((unsigned char)n.dt[0]) ? atoi(n.dt.c_str()) : 1;
+            if (n.channels < 1) n.channels = 1;
+            while (!n.dt.empty() && isdigit((unsigned char)n.dt[0])) n.dt.erase(0, 1);
+          } else if (k2 == "data") {
+            for (const std::string& s : split_flow(gather_flow(v2, i))) n.values.push_back(yaml_number(s));
+          }
+        }
+        if (n.rows < 0 || n.cols < 0 || n.values.size() != (size_t)n.rows * n.cols * n.channels) {
+          err = "matrix " + key + ": rows*cols does not match data";
+          return false;
+        }
+      } else if (!rest.empty() && rest[0] == '[') {
+        n.kind = FileNode::SEQ;
+        n.seq = split_flow(gather_flow(rest, i));
+      } else if (rest.empty() || rest[0] == '#') {
+        const size_t j = next_content(i);
+        if (j < lines.size() && trim(lines[j])[0] == '-' && indent_of(lines[j]) >= indent) {  // block sequence
+          n.kind = FileNode::SEQ;
+          while (i < lines.size()) {
+            if (blank(lines[i])) { i++; continue; }
+            const std::string m = trim(lines[i]);
+            if (m[0] != '-' || indent_of(lines[i]) < indent) break;
+            i++;
+            n.seq.push_back(unquote(m.substr(1)));
+          }
+        } else if (j < lines.size() && indent_of(lines[j]) > indent) {  // nested mapping
+          i = j;
+          if (!parse_map(i, indent_of(lines[j]), n)) return false;
+        } else {
+          n.kind = FileNode::SEQ;  // "key:" with nothing below: an empty sequence
+        }
+      } else {
+        n.kind = FileNode::SCALAR;
+        n.scalar = unquote(rest);
+      }
+      bool replaced = false;
+      for (size_t k = 0; k < out.child_keys.size(); k++)
+        if (out.child_keys[k] == key) { out.child_nodes[k] = n; replaced = true; }
+      if (!replaced) { out.child_keys.push_back(key); out.child_nodes.push_back(n); }
+    }
+    return true;
+  }
+};
+}  // namespace
+
+bool FileStorage::open(const std::string& path) {
+  opened_ = false;
+  root_ = FileNode();
+  std::ifstream in(path.c_str());
+  if (!in) { err_ = "cannot open " + path; return false; }
+  YamlParser yp;
+  for (std::string l; std::getline(in, l);) {
+    if (!l.empty() && l.back() == '\r') l.pop_back();
+    if (yp.lines.empty() && l.size() >= 3 && (unsigned char)l[0] == 0xEF && (unsigned char)l[1] == 0xBB && (unsigned char)l[2] == 0xBF) l.erase(0, 3);
+    yp.lines.push_back(l);
+  }
+  size_t i = 0;
+  if (!yp.parse_map(i, 0, root_)) { err_ = yp.err; return false; }
   opened_ = true;
   return true;
 }
 
-const FileNode& FileStorage::operator[](const std::string& key) const {
+const FileNode& FileNode::operator[](const std::string& key) const {
   static const FileNode none;
-  auto it = nodes_.find(key);
-  return it == nodes_.end() ? none : it->second;
+  for (size_t k = 0; k < child_keys.size(); k++)
+    if (child_keys[k] == key) return child_nodes[k];
+  return none;
 }
 
-std::vector<std::string> FileStorage::keys() const {
-  std::vector<std::string> k;
-  for (auto& kv : nodes_) k.push_back(kv.first);
-  return k;
-}
+const FileNode& FileStorage::operator[](const std::string& key) const { return root_[key]; }
 
-void operator>>(const FileNode& n, int& v) { v = n.kind == FileNode::SCALAR ? (int)strtol(n.scalar.c_str(), nullptr, 10) : 0; }
-void operator>>(const FileNode& n, double& v) { v = n.kind == FileNode::SCALAR ? strtod(n.scalar.c_str(), nullptr) : 0.0; }
+std::vector<std::string> FileStorage::keys() const { return root_.child_keys; }
+
+void operator>>(const FileNode& n, int& v) {  // cv::FileNode rounds a real to the nearest integer
+  if (n.kind != FileNode::SCALAR) { v = 0; return; }
+  char* e = nullptr;
+  const long l = strtol(n.scalar.c_str(), &e, 10);
+  v = (e && *e == 0) ? (int)l : (int)lrint(yaml_number(n.scalar));
+}
+void operator>>(const FileNode& n, double& v) { v = n.kind == FileNode::SCALAR ? yaml_number(n.scalar) : 0.0; }
 void operator>>(const FileNode& n, std::string& v) { v = n.kind == FileNode::SCALAR ? n.scalar : std::string(); }
 void operator>>(const FileNode& n, std::vector<std::string>& v) {
   v.clear();
@@ -172,8 +233,14 @@ void operator>>(const FileNode& n, std::vector<std::string>& v) {
 }
 void operator>>(const FileNode& n, Mat& m) {
   m.release();
-  if (n.kind != FileNode::MATRIX || n.rows <= 0 || n.cols <= 0 || n.values.size() < (size_t)n.rows * n.cols) return;
+  if (n.kind != FileNode::MATRIX || n.rows <= 0 || n.cols <= 0 || n.values.size() < (size_t)n.rows * n.cols * n.channels) return;
   const bool u8 = n.dt == "u";
+  if (n.channels == 3 && u8) {
+    m.create(n.rows, n.cols, SB_8UC3);
+    for (size_t k = 0; k < n.values.size(); k++) m.data[k] = (uint8_t)n.values[k];
+    return;
+  }
+  if (n.channels != 1) return;  // no multi-channel real matrices in this mirror
   m.create(n.rows, n.cols, u8 ? SB_8UC1 : SB_64FC1);
   for (int r = 0; r < n.rows; r++)
     for (int c = 0; c < n.cols; c++) {

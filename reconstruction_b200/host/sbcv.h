@@ -47,24 +47,29 @@ class Mat {
 };
 
 // Reader for the OpenCV "%YAML:1.0" dialect the reference's config.yml / calib_camera.yml use
-// (CManageData.cpp:26-66; writer example BatchProcess/main.cpp:47-73): top-level scalars, string
-// sequences (block "- x" or flow "[a, b]") and !!opencv-matrix nodes (dt u / i / f / d).
+// (CManageData.cpp:26-66; writer example BatchProcess/main.cpp:47-73): scalars (plain or quoted, .Inf / .Nan), string
+// sequences (block "- x" or flow "[a, b]", possibly over several lines), nested mappings and !!opencv-matrix nodes
+// (dt u / c / w / s / i / f / d with an optional channel count, e.g. "3u").  Pinned against files written by cv::FileStorage
+// (tests/test_host_decode.py).
 class FileNode {
  public:
-  enum Kind { NONE, SCALAR, SEQ, MATRIX };
+  enum Kind { NONE, SCALAR, SEQ, MATRIX, MAP };
   Kind kind = NONE;
   std::string scalar;
   std::vector<std::string> seq;
-  int rows = 0, cols = 0;
+  int rows = 0, cols = 0, channels = 1;
   std::string dt;
   std::vector<double> values;
+  std::vector<std::string> child_keys;  // MAP: children in file order
+  std::vector<FileNode> child_nodes;
   bool empty() const { return kind == NONE; }
+  const FileNode& operator[](const std::string& key) const;
 };
 void operator>>(const FileNode& n, int& v);
 void operator>>(const FileNode& n, double& v);
 void operator>>(const FileNode& n, std::string& v);
 void operator>>(const FileNode& n, std::vector<std::string>& v);
-void operator>>(const FileNode& n, Mat& m);  // dt u -> 8UC1, anything else -> 64FC1
+void operator>>(const FileNode& n, Mat& m);  // dt u -> 8UC1, 3u -> 8UC3, any other single-channel type -> 64FC1
 
 class FileStorage {
  public:
@@ -75,17 +80,23 @@ class FileStorage {
   bool isOpened() const { return opened_; }
   const FileNode& operator[](const std::string& key) const;
   const std::string& error() const { return err_; }
-  std::vector<std::string> keys() const;
+  std::vector<std::string> keys() const;  // top-level keys in file order
 
  private:
   bool opened_ = false;
   std::string err_;
-  std::map<std::string, FileNode> nodes_;
+  FileNode root_;
 };
 
 // Binary PNM (P5 grey / P6 colour, maxval 255) <-> Mat.  P6 is RGB on disk and BGR in memory (cv::imread
 // order).  imread(..., grayscale=true) converts colour input with the BT.601 weights cv::imread uses.
 bool imread_pnm(const std::string& path, Mat& out, bool grayscale);
 bool imwrite_pnm(const std::string& path, const Mat& m);
+
+// cv::imread stand-in (sbimg.cpp): JPEG (baseline), PNG, BMP and PNM by content; BGR or grey 8-bit output, the same bits
+// OpenCV produces for the file.  `grayscale` = the CV_LOAD_IMAGE_GRAYSCALE flag the reference reads its masks with.
+bool imread(const std::string& path, Mat& out, bool grayscale);
+bool imdecode(const uint8_t* bytes, size_t n, Mat& out, bool grayscale);
+const std::string& imread_error();  // why the last imread / imdecode of this thread failed
 
 }  // namespace sbcv

@@ -1,0 +1,687 @@
+// sbimg.cpp — native decoders for the image files either side of the path.
+//
+// The reference reads every frame and mask with cv::imread (CStereoMatching.cpp:147-151 colour, mask with
+// CV_LOAD_IMAGE_GRAYSCALE; CManageData.cpp:68 for the original size); its data sets are JPEG files
+// ("%.4d_Cam%d.jpg", BatchProcess/main.cpp:66).  OpenCV's codecs are third-party code that is not under /root/reference
+// (OpenCV 2.4.5 wraps libjpeg / libpng), so this restates the published algorithms and is pinned against the OpenCV
+// 4.13 build of this image (libjpeg-turbo, libpng): tests/test_host_decode.py compares bit for bit.
+//   JPEG  baseline / extended sequential Huffman, 8 bit, 1 or 3 components, any scan layout, restart intervals.
+//         Inverse DCT = the "islow" integer LL&M transform, chroma by "fancy" (triangle) upsampling, YCbCr -> RGB by the
+//         16-bit fixed-point tables: libjpeg's default decompression path.  Grey output of a colour file = the Y plane
+//         (what cv::imread(..., 0) asks libjpeg for).  Progressive and arithmetic-coded files are refused.
+//   PNG   all colour types, bit depths 1-16, Adam7 interlace; 16 -> 8 bit by dropping the low byte, alpha dropped, grey from
+//         RGB by libpng's 15-bit coefficients for the 0.299 / 0.587 OpenCV passes.
+//   BMP   uncompressed 24 / 32 bit.       PNM   P5 / P6 (sbcv.cpp).
+// EXIF orientation is ignored (as OpenCV 2.4.5 did).
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "sbcv.h"
+
+namespace sbcv {
+namespace {
+
+// =================================================================================================== JPEG
+const uint8_t kZigzag[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                             41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                             30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+
+struct Huff {
+  bool present = false;
+  uint8_t bits[17] = {0};
+  uint8_t vals[256] = {0};
+  // canonical decoding tables (ITU T.81 F.2.2.3)
+  int mincode[17], maxcode[18], valptr[17];
+  uint16_t fast[512];  // 9-bit look-ahead: (length << 8) | symbol, 0 = longer code
+  void build() {
+    int code = 0, k = 0;
+    for (int l = 1; l <= 16; l++) {
+      valptr[l] = k;
+      mincode[l] = code;
+      code += bits[l];
+      k += bits[l];
+      maxcode[l] = bits[l] ? code - 1 : -1;
+      code <<= 1;
+    }
+    maxcode[17] = 0x7fffffff;
+    memset(fast, 0, sizeof fast);
+    code = 0; k = 0;
+    for (int l = 1; l <= 9; l++) {
+      for (int i = 0; i < bits[l]; i++, k++, code++) {
+        const int lo = code << (9 - l);
+        for (int j = 0; j < (1 << (9 - l)); j++) fast[lo + j] = (uint16_t)((l << 8) | vals[k]);
+      }
+      code <<= 1;
+    }
+  }
+};
+
+struct BitReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  uint64_t acc = 0;
+  int n = 0;
+  bool hit_marker = false;
+  void fill() {
+    while (n <= 56) {
+      int b = 0;
+      if (!hit_marker && p < end) {
+        b = *p;
+        if (b == 0xFF) {
+          if (p + 1 < end && p[1] == 0x00) p += 2;
+          else { hit_marker = true; b = 0; }  // a marker: feed zeros until the caller resynchronises
+        } else p++;
+      }
+      acc |= (uint64_t)b << (56 - n);
+      n += 8;
+    }
+  }
+  int peek(int k) { if (n < k) fill(); return (int)(acc >> (64 - k)); }
+  void skip(int k) { acc <<= k; n -= k; }
+  int get(int k) { if (k == 0) return 0; const int v = peek(k); skip(k); return v; }
+  void reset() { acc = 0; n = 0; hit_marker = false; }
+};
+
+inline int huff_decode(BitReader& br, const Huff& h) {
+  const int look = br.peek(16);
+  const uint16_t f = h.fast[look >> 7];
+  if (f) { br.skip(f >> 8); return f & 255; }
+  for (int l = 10; l <= 16; l++) {
+    const int code = look >> (16 - l);
+    if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) {
+      br.skip(l);
+      return h.vals[h.valptr[l] + code - h.mincode[l]];
+    }
+  }
+  br.skip(16);
+  return -1;
+}
+inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+
+struct Comp {
+  int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
+  int bw = 0, bh = 0;     // blocks allocated (padded to whole MCUs)
+  int dw = 0, dh = 0;     // downsampled_width / height (real samples)
+  int pitch = 0;
+  std::vector<uint8_t> plane;
+  int pred = 0;
+};
+
+// jidctint.c (jpeg_idct_islow): CONST_BITS 13, PASS1_BITS 2
+inline int64_t descale(int64_t x, int n) { return (x + ((int64_t)1 << (n - 1))) >> n; }
+inline uint8_t range_limit(int64_t x) {  // range_limit[(x) & RANGE_MASK] with the table centred on 128
+  const int i = (int)(x & 1023);
+  if (i < 128) return (uint8_t)(i + 128);
+  if (i < 512) return 255;
+  if (i < 896) return 0;
+  return (uint8_t)(i - 896);
+}
+void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int pitch) {
+  enum { F0_298 = 2446, F0_390 = 3196, F0_541 = 4433, F0_765 = 6270, F0_899 = 7373, F1_175 = 9633, F1_501 = 12299, F1_847 = 15137,
+         F1_961 = 16069, F2_053 = 16819, F2_562 = 20995, F3_072 = 25172 };
+  int64_t ws[64];
+  for (int c = 0; c < 8; c++) {
+    int64_t in[8];
+    for (int r = 0; r < 8; r++) in[r] = (int64_t)coef[r * 8 + c] * q[r * 8 + c];
+    if ((in[1] | in[2] | in[3] | in[4] | in[5] | in[6] | in[7]) == 0) {
+      const int64_t dc = in[0] * 4;
+      for (int r = 0; r < 8; r++) ws[r * 8 + c] = dc;
+      continue;
+    }
+    int64_t z2 = in[2], z3 = in[6];
+    int64_t z1 = (z2 + z3) * F0_541;
+    int64_t tmp2 = z1 + z3 * -(int64_t)F1_847, tmp3 = z1 + z2 * F0_765;
+    z2 = in[0]; z3 = in[4];
+    int64_t tmp0 = (z2 + z3) * 8192, tmp1 = (z2 - z3) * 8192;
+    const int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = in[7]; tmp1 = in[5]; tmp2 = in[3]; tmp3 = in[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int64_t z4 = tmp1 + tmp3;
+    const int64_t z5 = (z3 + z4) * F1_175;
+    tmp0 *= F0_298; tmp1 *= F2_053; tmp2 *= F3_072; tmp3 *= F1_501;
+    z1 *= -(int64_t)F0_899; z2 *= -(int64_t)F2_562; z3 *= -(int64_t)F1_961; z4 *= -(int64_t)F0_390;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    ws[0 * 8 + c] = descale(tmp10 + tmp3, 11); ws[7 * 8 + c] = descale(tmp10 - tmp3, 11);
+    ws[1 * 8 + c] = descale(tmp11 + tmp2, 11); ws[6 * 8 + c] = descale(tmp11 - tmp2, 11);
+    ws[2 * 8 + c] = descale(tmp12 + tmp1, 11); ws[5 * 8 + c] = descale(tmp12 - tmp1, 11);
+    ws[3 * 8 + c] = descale(tmp13 + tmp0, 11); ws[4 * 8 + c] = descale(tmp13 - tmp0, 11);
+  }
+  for (int r = 0; r < 8; r++) {
+    const int64_t* w = ws + r * 8;
+    uint8_t* o = out + (size_t)r * pitch;
+    int64_t z2 = w[2], z3 = w[6];
+    int64_t z1 = (z2 + z3) * F0_541;
+    int64_t tmp2 = z1 + z3 * -(int64_t)F1_847, tmp3 = z1 + z2 * F0_765;
+    int64_t tmp0 = (w[0] + w[4]) * 8192, tmp1 = (w[0] - w[4]) * 8192;
+    const int64_t tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = w[7]; tmp1 = w[5]; tmp2 = w[3]; tmp3 = w[1];
+    z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
+    int64_t z4 = tmp1 + tmp3;
+    const int64_t z5 = (z3 + z4) * F1_175;
+    tmp0 *= F0_298; tmp1 *= F2_053; tmp2 *= F3_072; tmp3 *= F1_501;
+    z1 *= -(int64_t)F0_899; z2 *= -(int64_t)F2_562; z3 *= -(int64_t)F1_961; z4 *= -(int64_t)F0_390;
+    z3 += z5; z4 += z5;
+    tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
+    o[0] = range_limit(descale(tmp10 + tmp3, 18)); o[7] = range_limit(descale(tmp10 - tmp3, 18));
+    o[1] = range_limit(descale(tmp11 + tmp2, 18)); o[6] = range_limit(descale(tmp11 - tmp2, 18));
+    o[2] = range_limit(descale(tmp12 + tmp1, 18)); o[5] = range_limit(descale(tmp12 - tmp1, 18));
+    o[3] = range_limit(descale(tmp13 + tmp0, 18)); o[4] = range_limit(descale(tmp13 - tmp0, 18));
+  }
+}
+
+struct Jpeg {
+  const uint8_t* d;
+  size_t n;
+  std::string err;
+  int W = 0, H = 0, nc = 0, hmax = 1, vmax = 1, restart = 0;
+  bool adobe = false;
+  int adobe_transform = -1;
+  Comp comp[3];
+  uint16_t qt[4][64];
+  bool qt_set[4] = {false, false, false, false};
+  Huff hdc[4], hac[4];
+
+  static int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+  bool decode_block(BitReader& br, Comp& c, int16_t* coef) {
+    memset(coef, 0, 64 * sizeof(int16_t));
+    const Huff& dc = hdc[c.td];
+    const Huff& ac = hac[c.ta];
+    int s = huff_decode(br, dc);
+    if (s < 0 || s > 15) return false;
+    const int diff = s ? extend(br.get(s), s) : 0;
+    c.pred += diff;
+    coef[0] = (int16_t)c.pred;
+    for (int k = 1; k < 64;) {
+      const int rs = huff_decode(br, ac);
+      if (rs < 0) return false;
+      const int r = rs >> 4;
+      s = rs & 15;
+      if (s == 0) {
+        if (r != 15) break;
+        k += 16;
+        continue;
+      }
+      k += r;
+      if (k > 63) return false;
+      coef[kZigzag[k]] = (int16_t)extend(br.get(s), s);
+      k++;
+    }
+    return true;
+  }
+
+  // one scan: `sc` lists component indices.  Interleaved scans walk MCUs; a single-component scan walks that component's own
+  // blocks (ceil(dw / 8) x ceil(dh / 8), T.81 A.2.2)
+  bool scan(const uint8_t*& p, const std::vector<int>& sc) {
+    BitReader br;
+    br.p = p; br.end = d + n;
+    for (int ci : sc) comp[ci].pred = 0;
+    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+    const bool inter = sc.size() > 1;
+    Comp& c0 = comp[sc[0]];
+    const int ux = inter ? mcux : (c0.dw + 7) / 8, uy = inter ? mcuy : (c0.dh + 7) / 8;
+    int16_t coef[64];
+    int until_restart = restart;
+    for (int my = 0; my < uy; my++)
+      for (int mx = 0; mx < ux; mx++) {
+        if (restart && until_restart == 0) {  // expect RSTn
+          br.reset();
+          const uint8_t* q = br.p;
+          while (q + 1 < d + n && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+          if (q + 1 >= d + n) { err = "missing restart marker"; return false; }
+          br.p = q + 2;
+          for (int ci : sc) comp[ci].pred = 0;
+          until_restart = restart;
+        }
+        for (int ci : sc) {
+          Comp& c = comp[ci];
+          const int nh = inter ? c.h : 1, nv = inter ? c.v : 1;
+          for (int by = 0; by < nv; by++)
+            for (int bx = 0; bx < nh; bx++) {
+              if (!decode_block(br, c, coef)) { err = "corrupt entropy-coded data"; return false; }
+              const int X = mx * nh + bx, Y = my * nv + by;
+              if (X < c.bw && Y < c.bh) idct_islow(coef, qt[c.tq], c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8, c.pitch);
+            }
+        }
+        if (restart) until_restart--;
+      }
+    // position after the entropy-coded segment: the next marker
+    const uint8_t* q = br.p;
+    if (br.hit_marker) { /* p points at the 0xFF of the marker */ }
+    while (q + 1 < d + n && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
+    p = q;
+    return true;
+  }
+
+  bool parse() {
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) { err = "not a JPEG file"; return false; }
+    const uint8_t* p = d + 2;
+    const uint8_t* end = d + n;
+    bool have_sof = false;
+    int scans = 0;
+    while (p + 4 <= end) {
+      if (p[0] != 0xFF) { p++; continue; }
+      const int m = p[1];
+      if (m == 0xFF) { p++; continue; }
+      p += 2;
+      if (m == 0xD9) break;  // EOI
+      if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+      if (p + 2 > end) break;
+      const int len = be16(p);
+      if (len < 2 || p + len > end) { err = "truncated segment"; return false; }
+      const uint8_t* s = p + 2;
+      const uint8_t* se = p + len;
+      if (m == 0xDB) {  // DQT
+        while (s < se) {
+          const int pq = s[0] >> 4, tq = s[0] & 15;
+          s++;
+          if (tq > 3 || s + (pq ? 128 : 64) > se) { err = "bad DQT"; return false; }
+          for (int i = 0; i < 64; i++) {
+            qt[tq][kZigzag[i]] = (uint16_t)(pq ? be16(s) : s[0]);
+            s += pq ? 2 : 1;
+          }
+          qt_set[tq] = true;
+        }
+      } else if (m == 0xC4) {  // DHT
+        while (s < se) {
+          const int tc = s[0] >> 4, th = s[0] & 15;
+          s++;
+          if (tc > 1 || th > 3 || s + 16 > se) { err = "bad DHT"; return false; }
+          Huff& h = tc ? hac[th] : hdc[th];
+          int cnt = 0;
+          h.bits[0] = 0;
+          for (int i = 1; i <= 16; i++) { h.bits[i] = s[i - 1]; cnt += s[i - 1]; }
+          s += 16;
+          if (cnt > 256 || s + cnt > se) { err = "bad DHT"; return false; }
+          memcpy(h.vals, s, cnt);
+          s += cnt;
+          h.present = true;
+          h.build();
+        }
+      } else if (m == 0xC0 || m == 0xC1) {  // SOF0 / SOF1
+        if (len < 8 || s[0] != 8) { err = "only 8-bit JPEG is supported"; return false; }
+        H = be16(s + 1); W = be16(s + 3); nc = s[5];
+        if (W <= 0 || H <= 0 || (nc != 1 && nc != 3) || len < 8 + 3 * nc) { err = "unsupported JPEG frame (components)"; return false; }
+        for (int i = 0; i < nc; i++) {
+          comp[i].id = s[6 + 3 * i];
+          comp[i].h = s[7 + 3 * i] >> 4;
+          comp[i].v = s[7 + 3 * i] & 15;
+          comp[i].tq = s[8 + 3 * i];
+          if (comp[i].h < 1 || comp[i].h > 4 || comp[i].v < 1 || comp[i].v > 4 || comp[i].tq > 3) { err = "bad SOF"; return false; }
+          hmax = comp[i].h > hmax ? comp[i].h : hmax;
+          vmax = comp[i].v > vmax ? comp[i].v : vmax;
+        }
+        const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+        for (int i = 0; i < nc; i++) {
+          Comp& c = comp[i];
+          c.bw = mcux * c.h; c.bh = mcuy * c.v;
+          c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;
+          c.pitch = c.bw * 8;
+          c.plane.assign((size_t)c.pitch * c.bh * 8, 0);
+        }
+        have_sof = true;
+      } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+        err = m == 0xC2 ? "progressive JPEG is not supported" : "unsupported JPEG coding process";
+        return false;
+      } else if (m == 0xDD) {
+        if (len >= 4) restart = be16(s);
+      } else if (m == 0xEE) {  // Adobe
+        if (len >= 14 && memcmp(s, "Adobe", 5) == 0) { adobe = true; adobe_transform = s[11]; }
+      } else if (m == 0xDA) {  // SOS
+        if (!have_sof) { err = "SOS before SOF"; return false; }
+        const int ns = s[0];
+        if (ns < 1 || ns > nc || len < 6 + 2 * ns) { err = "bad SOS"; return false; }
+        std::vector<int> sc;
+        for (int i = 0; i < ns; i++) {
+          int ci = -1;
+          for (int k = 0; k < nc; k++) if (comp[k].id == s[1 + 2 * i]) ci = k;
+          if (ci < 0) { err = "bad SOS component"; return false; }
+          comp[ci].td = s[2 + 2 * i] >> 4;
+          comp[ci].ta = s[2 + 2 * i] & 15;
+          if (comp[ci].td > 3 || comp[ci].ta > 3 || !hdc[comp[ci].td].present || !hac[comp[ci].ta].present || !qt_set[comp[ci].tq]) {
+            err = "scan refers to a missing table";
+            return false;
+          }
+          sc.push_back(ci);
+        }
+        p += len;
+        if (!scan(p, sc)) return false;
+        scans++;
+        continue;
+      }
+      p += len;
+    }
+    if (!have_sof || scans == 0) { err = "no image data"; return false; }
+    return true;
+  }
+
+  // jdsample.c: fancy (triangle) upsampling where libjpeg uses it (downsampled_width > 2), replication otherwise.
+  // Rows above the first / below the last real sample row replicate it (jdmainct.c context rows).
+  void upsample(const Comp& c, std::vector<uint8_t>& out) const {
+    const int ow = W, oh = H;
+    out.assign((size_t)ow * oh, 0);
+    const int hx = hmax / c.h, vx = vmax / c.v;
+    const bool exact = hmax % c.h == 0 && vmax % c.v == 0;
+    const int n = c.dw;
+    auto row = [&](int r) { r = r < 0 ? 0 : (r >= c.dh ? c.dh - 1 : r); return c.plane.data() + (size_t)r * c.pitch; };
+    if (exact && hx == 1 && vx == 1) {
+      for (int y = 0; y < oh; y++) memcpy(out.data() + (size_t)y * ow, row(y), ow);
+      return;
+    }
+    const bool fancy = n > 2;
+    std::vector<uint8_t> line((size_t)2 * n + 4);
+    if (exact && fancy && hx == 2 && vx == 1) {  // h2v1_fancy_upsample
+      for (int y = 0; y < oh; y++) {
+        const uint8_t* in = row(y);
+        line[0] = in[0];
+        line[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+        for (int i = 1; i < n - 1; i++) {
+          const int v = in[i] * 3;
+          line[2 * i] = (uint8_t)((v + in[i - 1] + 1) >> 2);
+          line[2 * i + 1] = (uint8_t)((v + in[i + 1] + 2) >> 2);
+        }
+        line[2 * n - 2] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
+        line[2 * n - 1] = in[n - 1];
+        memcpy(out.data() + (size_t)y * ow, line.data(), ow);
+      }
+      return;
+    }
+    if (exact && fancy && hx == 2 && vx == 2) {  // h2v2_fancy_upsample
+      for (int y = 0; y < oh; y++) {
+        const int r = y >> 1;
+        const uint8_t* in0 = row(r);
+        const uint8_t* in1 = row((y & 1) ? r + 1 : r - 1);
+        int thiscol = in0[0] * 3 + in1[0], nextcol = in0[1] * 3 + in1[1], lastcol;
+        line[0] = (uint8_t)((thiscol * 4 + 8) >> 4);
+        line[1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+        lastcol = thiscol; thiscol = nextcol;
+        for (int i = 1; i < n - 1; i++) {
+          nextcol = in0[i + 1] * 3 + in1[i + 1];
+          line[2 * i] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+          line[2 * i + 1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
+          lastcol = thiscol; thiscol = nextcol;
+        }
+        line[2 * n - 2] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
+        line[2 * n - 1] = (uint8_t)((thiscol * 4 + 7) >> 4);
+        memcpy(out.data() + (size_t)y * ow, line.data(), ow);
+      }
+      return;
+    }
+    if (exact && hx == 1 && vx == 2) {  // h1v2_fancy_upsample (libjpeg-turbo; no width condition)
+      for (int y = 0; y < oh; y++) {
+        const int r = y >> 1;
+        const uint8_t* in0 = row(r);
+        const uint8_t* in1 = row((y & 1) ? r + 1 : r - 1);
+        const int bias = (y & 1) ? 2 : 1;
+        uint8_t* o = out.data() + (size_t)y * ow;
+        for (int x = 0; x < ow; x++) o[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
+      }
+      return;
+    }
+    // replication (int_upsample / h2v1_upsample / h2v2_upsample); non-integral ratios are approximated the same way
+    for (int y = 0; y < oh; y++) {
+      const uint8_t* in = row(exact ? y / vx : y * c.v / vmax);
+      uint8_t* o = out.data() + (size_t)y * ow;
+      for (int x = 0; x < ow; x++) {
+        int sx = exact ? x / hx : x * c.h / hmax;
+        if (sx >= n) sx = n - 1;
+        o[x] = in[sx];
+      }
+    }
+  }
+
+  bool to_mat(Mat& out, bool gray) {
+    std::vector<uint8_t> pl[3];
+    const bool rgb_coded = nc == 3 && ((adobe && adobe_transform == 0) || (!adobe && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B'));
+    if (gray) {
+      if (rgb_coded) { err = "grey output of an RGB-coded JPEG is not supported"; return false; }
+      upsample(comp[0], pl[0]);  // luma is never subsampled in practice; handled anyway
+      out.create(H, W, SB_8UC1);
+      memcpy(out.data, pl[0].data(), (size_t)W * H);
+      return true;
+    }
+    out.create(H, W, SB_8UC3);
+    if (nc == 1) {
+      upsample(comp[0], pl[0]);
+      for (size_t i = 0; i < (size_t)W * H; i++) out.data[3 * i] = out.data[3 * i + 1] = out.data[3 * i + 2] = pl[0][i];
+      return true;
+    }
+    for (int i = 0; i < 3; i++) upsample(comp[i], pl[i]);
+    if (rgb_coded) {
+      for (size_t i = 0; i < (size_t)W * H; i++) { out.data[3 * i] = pl[2][i]; out.data[3 * i + 1] = pl[1][i]; out.data[3 * i + 2] = pl[0][i]; }
+      return true;
+    }
+    // jdcolor.c build_ycc_rgb_table / ycc_rgb_convert: SCALEBITS 16
+    int cr_r[256], cb_b[256];
+    long cr_g[256], cb_g[256];
+    for (int i = 0; i < 256; i++) {
+      const long x = i - 128;
+      cr_r[i] = (int)((91881L * x + 32768L) >> 16);    // FIX(1.40200)
+      cb_b[i] = (int)((116130L * x + 32768L) >> 16);   // FIX(1.77200)
+      cr_g[i] = -46802L * x;                           // FIX(0.71414)
+      cb_g[i] = -22554L * x + 32768L;                  // FIX(0.34414)
+    }
+    auto clamp = [](int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+      const int y = pl[0][i], cb = pl[1][i], cr = pl[2][i];
+      out.data[3 * i + 2] = clamp(y + cr_r[cr]);
+      out.data[3 * i + 1] = clamp(y + (int)((cb_g[cb] + cr_g[cr]) >> 16));
+      out.data[3 * i + 0] = clamp(y + cb_b[cb]);
+    }
+    return true;
+  }
+};
+
+// =================================================================================================== PNG
+uint32_t be32(const uint8_t* p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+bool png_decode(const uint8_t* d, size_t n, Mat& out, bool gray, std::string& err) {
+  static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+  if (n < 8 || memcmp(d, sig, 8) != 0) { err = "not a PNG file"; return false; }
+  size_t p = 8;
+  uint32_t W = 0, H = 0;
+  int depth = 0, ctype = 0, interlace = 0;
+  std::vector<uint8_t> idat, plte;
+  while (p + 12 <= n) {
+    const uint32_t len = be32(d + p);
+    const uint8_t* type = d + p + 4;
+    if (p + 12 + (size_t)len > n) { err = "truncated PNG chunk"; return false; }
+    const uint8_t* body = d + p + 8;
+    if (memcmp(type, "IHDR", 4) == 0 && len >= 13) {
+      W = be32(body); H = be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
+    } else if (memcmp(type, "PLTE", 4) == 0) {
+      plte.assign(body, body + len);
+    } else if (memcmp(type, "IDAT", 4) == 0) {
+      idat.insert(idat.end(), body, body + len);
+    } else if (memcmp(type, "IEND", 4) == 0) {
+      break;
+    }
+    p += 12 + (size_t)len;
+  }
+  if (W == 0 || H == 0 || W > 65535 || H > 65535) { err = "bad PNG header"; return false; }
+  const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 3 ? 1 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (!ch || (depth != 1 && depth != 2 && depth != 4 && depth != 8 && depth != 16) || (ctype == 3 && depth == 16) ||
+      ((ctype == 2 || ctype == 4 || ctype == 6) && depth < 8) || interlace > 1) { err = "unsupported PNG format"; return false; }
+  const int bpp_bits = ch * depth, bpp = bpp_bits >= 8 ? bpp_bits / 8 : 1;
+  auto row_bytes = [&](uint32_t w) { return ((size_t)w * bpp_bits + 7) / 8; };
+  // passes: (x0, y0, dx, dy)
+  static const int adam7[7][4] = {{0, 0, 8, 8}, {4, 0, 8, 8}, {0, 4, 4, 8}, {2, 0, 4, 4}, {0, 2, 2, 4}, {1, 0, 2, 2}, {0, 1, 1, 2}};
+  size_t raw_size = 0;
+  const int npass = interlace ? 7 : 1;
+  uint32_t pw[7], ph[7];
+  for (int i = 0; i < npass; i++) {
+    pw[i] = interlace ? (W - adam7[i][0] + adam7[i][2] - 1) / adam7[i][2] : W;
+    ph[i] = interlace ? (H - adam7[i][1] + adam7[i][3] - 1) / adam7[i][3] : H;
+    if (interlace && ((int)W <= adam7[i][0] || (int)H <= adam7[i][1])) pw[i] = ph[i] = 0;
+    if (pw[i] && ph[i]) raw_size += (row_bytes(pw[i]) + 1) * ph[i];
+  }
+  std::vector<uint8_t> raw(raw_size);
+  {
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit(&zs) != Z_OK) { err = "zlib init failed"; return false; }
+    zs.next_in = idat.data(); zs.avail_in = (uInt)idat.size();
+    zs.next_out = raw.data(); zs.avail_out = (uInt)raw.size();
+    const int rc = inflate(&zs, Z_FINISH);
+    const size_t got = zs.total_out;
+    inflateEnd(&zs);
+    if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || got != raw.size()) { err = "PNG data does not inflate to the image size"; return false; }
+  }
+  // sample (x, y, channel) as 8-bit after the conversions OpenCV asks libpng for
+  std::vector<uint16_t> px((size_t)W * H * 4, 255);  // RGBA, full sample width (alpha unused)
+  size_t off = 0;
+  for (int ps = 0; ps < npass; ps++) {
+    if (!pw[ps] || !ph[ps]) continue;
+    const size_t rb = row_bytes(pw[ps]);
+    std::vector<uint8_t> prev(rb, 0);
+    for (uint32_t y = 0; y < ph[ps]; y++) {
+      const int ft = raw[off];
+      uint8_t* cur = raw.data() + off + 1;
+      for (size_t i = 0; i < rb; i++) {
+        const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
+        int pred = 0;
+        switch (ft) {
+          case 0: break;
+          case 1: pred = a; break;
+          case 2: pred = b; break;
+          case 3: pred = (a + b) >> 1; break;
+          case 4: {
+            const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
+            pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+            break;
+          }
+          default: err = "bad PNG filter"; return false;
+        }
+        cur[i] = (uint8_t)(cur[i] + pred);
+      }
+      memcpy(prev.data(), cur, rb);
+      const uint32_t Y = interlace ? adam7[ps][1] + y * adam7[ps][3] : y;
+      for (uint32_t x = 0; x < pw[ps]; x++) {
+        const uint32_t X = interlace ? adam7[ps][0] + x * adam7[ps][2] : x;
+        uint16_t* o = px.data() + ((size_t)Y * W + X) * 4;
+        uint16_t s[4] = {0, 0, 0, 255};
+        for (int k = 0; k < ch; k++) {
+          if (depth == 8) s[k] = cur[(size_t)x * ch + k];
+          else if (depth == 16) s[k] = (uint16_t)((cur[((size_t)x * ch + k) * 2] << 8) | cur[((size_t)x * ch + k) * 2 + 1]);
+          else {
+            const size_t bit = (size_t)x * depth;
+            const int v = (cur[bit >> 3] >> (8 - depth - (bit & 7))) & ((1 << depth) - 1);
+            s[k] = ctype == 3 ? (uint8_t)v : (uint8_t)(v * 255 / ((1 << depth) - 1));
+          }
+        }
+        if (ctype == 3) {
+          const size_t idx = s[0];
+          if (idx * 3 + 2 < plte.size()) { o[0] = plte[idx * 3]; o[1] = plte[idx * 3 + 1]; o[2] = plte[idx * 3 + 2]; }
+          else o[0] = o[1] = o[2] = 0;
+        } else if (ch <= 2) { o[0] = o[1] = o[2] = s[0]; }
+        else { o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; }
+      }
+      off += rb + 1;
+    }
+  }
+  const bool colour_src = ctype == 2 || ctype == 6 || ctype == 3;
+  if (gray) {
+    out.create((int)H, (int)W, SB_8UC1);
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+      const long r = px[4 * i], g = px[4 * i + 1], b = px[4 * i + 2];
+      // png_set_rgb_to_gray(png, 1, 0.299, 0.587): 15-bit coefficients 9797 / 19234 / 3737 (libpng truncates them); 8-bit samples
+      // are not rounded, 16-bit samples are (and are converted before png_set_strip_16 drops the low byte); equal channels pass
+      long v = r;
+      if (colour_src && !(r == g && g == b)) v = depth == 16 ? (9797 * r + 19234 * g + 3737 * b + 16384) >> 15 : (9797 * r + 19234 * g + 3737 * b) >> 15;
+      out.data[i] = (uint8_t)(depth == 16 ? v >> 8 : v);
+    }
+  } else {
+    out.create((int)H, (int)W, SB_8UC3);
+    const int sh = depth == 16 ? 8 : 0;  // png_set_strip_16: the high byte
+    for (size_t i = 0; i < (size_t)W * H; i++) {
+      out.data[3 * i] = (uint8_t)(px[4 * i + 2] >> sh); out.data[3 * i + 1] = (uint8_t)(px[4 * i + 1] >> sh); out.data[3 * i + 2] = (uint8_t)(px[4 * i] >> sh);
+    }
+  }
+  return true;
+}
+
+// =================================================================================================== BMP
+bool bmp_decode(const uint8_t* d, size_t n, Mat& out, bool gray, std::string& err) {
+  auto le32 = [&](size_t o) { return (uint32_t)d[o] | (d[o + 1] << 8) | (d[o + 2] << 16) | ((uint32_t)d[o + 3] << 24); };
+  auto le16 = [&](size_t o) { return (int)(d[o] | (d[o + 1] << 8)); };
+  if (n < 54 || d[0] != 'B' || d[1] != 'M') { err = "not a BMP file"; return false; }
+  const uint32_t offs = le32(10), hdr = le32(14);
+  if (hdr < 40) { err = "unsupported BMP header"; return false; }
+  const int W = (int)le32(18);
+  int H = (int)le32(22);
+  const int bpp = le16(28);
+  const uint32_t compr = le32(30);
+  const bool top_down = H < 0;
+  if (top_down) H = -H;
+  if (W <= 0 || H <= 0 || (bpp != 24 && bpp != 32) || (compr != 0 && !(compr == 3 && bpp == 32))) { err = "unsupported BMP format"; return false; }
+  const size_t stride = ((size_t)W * (bpp / 8) + 3) & ~(size_t)3;
+  if (offs + stride * H > n) { err = "truncated BMP"; return false; }
+  out.create(H, W, gray ? SB_8UC1 : SB_8UC3);
+  for (int y = 0; y < H; y++) {
+    const uint8_t* src = d + offs + stride * (top_down ? y : H - 1 - y);
+    uint8_t* o = out.ptr<uint8_t>(y);
+    for (int x = 0; x < W; x++) {
+      const int b = src[x * (bpp / 8)], g = src[x * (bpp / 8) + 1], r = src[x * (bpp / 8) + 2];
+      if (gray) o[x] = (uint8_t)((r * 4899 + g * 9617 + b * 1868 + (1 << 13)) >> 14);
+      else { o[3 * x] = (uint8_t)b; o[3 * x + 1] = (uint8_t)g; o[3 * x + 2] = (uint8_t)r; }
+    }
+  }
+  return true;
+}
+
+thread_local std::string g_imread_error;
+
+}  // namespace
+
+const std::string& imread_error() { return g_imread_error; }
+
+bool imdecode(const uint8_t* d, size_t n, Mat& out, bool grayscale) {
+  out.release();
+  g_imread_error.clear();
+  if (n >= 2 && d[0] == 0xFF && d[1] == 0xD8) {
+    Jpeg j;
+    j.d = d; j.n = n;
+    memset(j.qt, 0, sizeof j.qt);
+    if (!j.parse() || !j.to_mat(out, grayscale)) { g_imread_error = j.err; out.release(); return false; }
+    return true;
+  }
+  if (n >= 8 && d[0] == 0x89 && d[1] == 'P') {
+    if (!png_decode(d, n, out, grayscale, g_imread_error)) { out.release(); return false; }
+    return true;
+  }
+  if (n >= 2 && d[0] == 'B' && d[1] == 'M') {
+    if (!bmp_decode(d, n, out, grayscale, g_imread_error)) { out.release(); return false; }
+    return true;
+  }
+  g_imread_error = "unknown image format";
+  return false;
+}
+
+bool imread(const std::string& path, Mat& out, bool grayscale) {
+  out.release();
+  FILE* fp = fopen(path.c_str(), "rb");
+  if (!fp) { g_imread_error = "cannot open " + path; return false; }
+  uint8_t magic[2] = {0, 0};
+  const size_t got = fread(magic, 1, 2, fp);
+  if (got == 2 && magic[0] == 'P' && (magic[1] == '5' || magic[1] == '6')) {
+    fclose(fp);
+    return imread_pnm(path, out, grayscale);
+  }
+  fseek(fp, 0, SEEK_END);
+  const long sz = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  if (sz <= 0) { fclose(fp); g_imread_error = "empty file"; return false; }
+  std::vector<uint8_t> buf((size_t)sz);
+  const bool ok = fread(buf.data(), 1, buf.size(), fp) == buf.size();
+  fclose(fp);
+  if (!ok) { g_imread_error = "read error"; return false; }
+  return imdecode(buf.data(), buf.size(), out, grayscale);
+}
+
+}  // namespace sbcv

@@ -90,10 +90,11 @@ def write_dataset(root, pyrm_num, lowest_w, lowest_h, n_pairs=1, isoutput=0, pai
     return root + "config.yml", pairs
 
 
-def write_raw_dataset(root, pyrm_num, lowest_w, lowest_h, origin, cams, images, masks, pairs, isoutput=0):
-    """A data set of ORIGINAL (unrectified) frames in the reference's schema: config.yml, calib_camera.yml and one PNM image
+def write_raw_dataset(root, pyrm_num, lowest_w, lowest_h, origin, cams, images, masks, pairs, isoutput=0, fmt="pnm"):
+    """A data set of ORIGINAL (unrectified) frames in the reference's schema: config.yml, calib_camera.yml and one image
     + mask per camera.  The host mirror then runs Rectify natively (no staged/ directory).  cams: [(K, Rt)] per camera,
-    images / masks: per camera arrays at `origin` size, pairs: [[camA, camB], ...]."""
+    images / masks: per camera arrays at `origin` size, pairs: [[camA, camB], ...].  fmt: "pnm" (PPM / PGM), or "jpg" / "png"
+    written by OpenCV like the reference's own data sets ("%.4d_Cam%d.jpg", BatchProcess/main.cpp:66)."""
     os.makedirs(os.path.join(root, "mask"), exist_ok=True)
     root = os.path.join(os.path.abspath(root), "")
     with open(root + "calib_camera.yml", "w") as f:
@@ -101,11 +102,19 @@ def write_raw_dataset(root, pyrm_num, lowest_w, lowest_h, origin, cams, images, 
         for i, (k, rt) in enumerate(cams):
             f.write(_mat(f"intrinsic-{i}", k))
             f.write(_mat(f"extrinsic-{i}", rt))
-    names = [f"{1:04d}_Cam{i}.ppm" for i in range(len(cams))]
+    ext = {"pnm": ("ppm", "pgm"), "jpg": ("jpg", "jpg"), "png": ("png", "png")}[fmt]
+    names = [f"{1:04d}_Cam{i}.{ext[0]}" for i in range(len(cams))]
+    mask_names = [f"mask/{1:04d}_Cam{i}.{ext[1]}" for i in range(len(cams))]
     for i, n in enumerate(names):
         img = images[i] if images[i].ndim == 3 else np.repeat(images[i][:, :, None], 3, axis=2)
-        write_pnm(root + n, img)
-        write_pnm(root + "mask/" + n.replace(".ppm", ".pgm"), masks[i])
+        if fmt == "pnm":
+            write_pnm(root + n, img)
+            write_pnm(root + mask_names[i], masks[i])
+        else:
+            import cv2
+
+            par = [cv2.IMWRITE_JPEG_QUALITY, 95] if fmt == "jpg" else []
+            assert cv2.imwrite(root + n, np.ascontiguousarray(img), par) and cv2.imwrite(root + mask_names[i], np.ascontiguousarray(masks[i]), par)
     with open(root + "config.yml", "w") as f:
         f.write("%YAML:1.0\n---\n")
         f.write(f'filepath: "{root}"\n')
@@ -114,7 +123,7 @@ def write_raw_dataset(root, pyrm_num, lowest_w, lowest_h, origin, cams, images, 
         f.write("camera_calib_name: calib_camera.yml\n")
         f.write(f"PyrmNum: {pyrm_num}\nLowestLevelWidth: {lowest_w}\nLowestLevelHeight: {lowest_h}\n")
         f.write("imagelist:\n" + "".join(f'   - "{n}"\n' for n in names))
-        f.write("masklist:\n" + "".join(f'   - "mask/{n.replace(".ppm", ".pgm")}"\n' for n in names))
+        f.write("masklist:\n" + "".join(f'   - "{n}"\n' for n in mask_names))
         f.write(_mat("camID", np.array(pairs), dt="u"))
     return root + "config.yml"
 

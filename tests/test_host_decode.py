@@ -1,0 +1,226 @@
+"""Native readers of the host mirror, on CPU: the image decoders behind sbcv::imread (JPEG / PNG / BMP,
+reconstruction_b200/host/sbimg.cpp) and the OpenCV-YAML reader (sbcv.cpp) against OpenCV itself — bit for bit.
+The reference reads frames with cv::imread (CStereoMatching.cpp:147-151) and its configuration with cv::FileStorage
+(CManageData.cpp:26-66); OpenCV 4.13 as installed here is the pin (tests/golden/make_decode_golden.py wrote the fixtures)."""
+import json
+import os
+import struct
+import subprocess
+import zlib
+
+import numpy as np
+import pytest
+
+from reconstruction_b200 import capi
+
+HOST = os.path.join(os.path.dirname(capi.HERE), "reconstruction_b200", "host")
+BIN = os.path.join(HOST, "reconstruction")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "decode")
+
+
+@pytest.fixture(scope="module")
+def cli():
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    return BIN
+
+
+def read_pnm(path):
+    d = open(path, "rb").read()
+    magic, dims, _mx, body = d.split(b"\n", 3)
+    w, h = map(int, dims.split())
+    a = np.frombuffer(body, np.uint8)
+    return a.reshape(h, w, 3)[:, :, ::-1] if magic == b"P6" else a.reshape(h, w)
+
+
+def decode(cli, path, out, gray):
+    r = subprocess.run([cli, "--decode", path, out] + (["gray"] if gray else []), capture_output=True, text=True)
+    return (read_pnm(out) if r.returncode == 0 else None), r.stdout
+
+
+def test_golden_files(cli, tmp_path):
+    """Committed files + what OpenCV 4.13 decoded them to: no cv2 needed at test time."""
+    exp = np.load(os.path.join(GOLD, "decode_expected.npz"))
+    names = sorted({k.split(":")[0] for k in exp.files})
+    assert len(names) == 12
+    for name in names:
+        for mode in ("color", "gray"):
+            got, msg = decode(cli, os.path.join(GOLD, name), str(tmp_path / "o.pnm"), mode == "gray")
+            assert got is not None, (name, mode, msg)
+            assert got.shape == exp[f"{name}:{mode}"].shape and np.array_equal(got, exp[f"{name}:{mode}"]), (name, mode)
+
+
+def _texture(h, w, rng):
+    y, x = np.mgrid[0:h, 0:w]
+    img = np.stack([128 + 100 * np.sin(x / 7.0 + c) * np.cos(y / 5.0 - c) + rng.normal(0, 12, (h, w)) for c in range(3)], -1)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def _check_against_cv2(cli, tmp_path, data, tag):
+    import cv2
+
+    p = str(tmp_path / "t.bin")
+    open(p, "wb").write(data)
+    for gray in (False, True):
+        ref = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_GRAYSCALE if gray else cv2.IMREAD_COLOR)
+        got, msg = decode(cli, p, str(tmp_path / "o.pnm"), gray)
+        assert got is not None, (tag, gray, msg)
+        assert got.shape == ref.shape and np.array_equal(got, ref), (tag, gray)
+
+
+def test_jpeg_matches_opencv(cli, tmp_path):
+    """Sizes around the MCU edges x quality x every chroma layout x restart intervals; colour and grey (= Y plane) output."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    S = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+         cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    n = 0
+    for (h, w) in [(48, 64), (37, 53), (8, 8), (1, 1), (3, 2), (17, 16), (100, 33)]:
+        for q, sf, rst in [(50, S[0], 0), (90, S[1], 2), (100, S[2], 0), (75, S[3], 1), (85, S[4], 3), (95, S[0], 5)]:
+            ok, b = cv2.imencode(".jpg", _texture(h, w, rng), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf,
+                                                                cv2.IMWRITE_JPEG_RST_INTERVAL, rst])
+            assert ok
+            _check_against_cv2(cli, tmp_path, b.tobytes(), ("jpeg", h, w, q, hex(sf), rst))
+            n += 1
+    ok, b = cv2.imencode(".jpg", _texture(45, 31, rng)[..., 1], [cv2.IMWRITE_JPEG_QUALITY, 85])  # single-component file
+    _check_against_cv2(cli, tmp_path, b.tobytes(), "grey jpeg")
+    ok, b = cv2.imencode(".jpg", rng.integers(0, 256, (64, 80, 3), dtype=np.uint8), [cv2.IMWRITE_JPEG_OPTIMIZE, 1, cv2.IMWRITE_JPEG_QUALITY, 97])
+    _check_against_cv2(cli, tmp_path, b.tobytes(), "optimised tables, noise")
+    assert n == 42
+
+
+def test_progressive_jpeg_is_refused(cli, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    ok, b = cv2.imencode(".jpg", _texture(32, 32, np.random.default_rng(1)), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+    p = str(tmp_path / "p.jpg")
+    open(p, "wb").write(b.tobytes())
+    got, msg = decode(cli, p, str(tmp_path / "o.pnm"), False)
+    assert got is None and "progressive JPEG is not supported" in msg  # loud, never a silently wrong image
+
+
+def _chunk(t, d):
+    return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xFFFFFFFF)
+
+
+def _png(w, h, depth, ctype, raw, plte=None, interlace=0):
+    out = b"\x89PNG\r\n\x1a\n" + _chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, depth, ctype, 0, 0, interlace))
+    if plte is not None:
+        out += _chunk(b"PLTE", plte)
+    return out + _chunk(b"IDAT", zlib.compress(raw)) + _chunk(b"IEND", b"")
+
+
+def test_png_bmp_match_opencv(cli, tmp_path):
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    for shape, dt in [((33, 47, 3), np.uint8), ((33, 47), np.uint8), ((20, 21, 4), np.uint8), ((19, 23, 3), np.uint16), ((19, 23), np.uint16),
+                      ((1, 1, 3), np.uint8)]:
+        a = rng.integers(0, 65536 if dt == np.uint16 else 256, shape).astype(dt)
+        ok, b = cv2.imencode(".png", a)
+        _check_against_cv2(cli, tmp_path, b.tobytes(), ("png", shape, dt.__name__))
+    # hand-made streams: palette and grey at 8 / 4 / 2 / 1 bits, grey + alpha
+    w, h = 13, 7
+    pal = rng.integers(0, 256, (256, 3), dtype=np.uint8).tobytes()
+    for depth in (8, 4, 2, 1):
+        rb = (w * depth + 7) // 8
+        raw = b"".join(b"\0" + rng.integers(0, 256, rb, dtype=np.uint8).tobytes() for _ in range(h))
+        _check_against_cv2(cli, tmp_path, _png(w, h, depth, 3, raw, pal), ("palette", depth))
+        _check_against_cv2(cli, tmp_path, _png(w, h, depth, 0, raw), ("grey", depth))
+    raw = b"".join(b"\0" + rng.integers(0, 256, w * 2, dtype=np.uint8).tobytes() for _ in range(h))
+    _check_against_cv2(cli, tmp_path, _png(w, h, 8, 4, raw), "grey+alpha")
+    # every filter type (Sub / Up / Average / Paeth), applied by hand
+    img = rng.integers(0, 256, (9, 11, 3), dtype=np.uint8)
+    raw, prev = b"", np.zeros(33, np.int32)
+    for y in range(9):
+        cur = img[y].reshape(-1).astype(np.int32)
+        ft = 1 + y % 4
+        a = np.concatenate([np.zeros(3, np.int32), cur[:-3]])
+        c = np.concatenate([np.zeros(3, np.int32), prev[:-3]])
+        if ft == 1:
+            pred = a
+        elif ft == 2:
+            pred = prev
+        elif ft == 3:
+            pred = (a + prev) >> 1
+        else:
+            p = a + prev - c
+            pa, pb, pc = abs(p - a), abs(p - prev), abs(p - c)
+            pred = np.where((pa <= pb) & (pa <= pc), a, np.where(pb <= pc, prev, c))
+        raw += bytes([ft]) + ((cur - pred) & 255).astype(np.uint8).tobytes()
+        prev = cur
+    _check_against_cv2(cli, tmp_path, _png(11, 9, 8, 2, raw), "filters")
+    # Adam7
+    for shp in [(9, 11, 3), (3, 2, 3), (17, 5, 3), (1, 1, 3)]:
+        img = rng.integers(0, 256, shp, dtype=np.uint8)
+        raw = b""
+        for x0, y0, dx, dy in [(0, 0, 8, 8), (4, 0, 8, 8), (0, 4, 4, 8), (2, 0, 4, 4), (0, 2, 2, 4), (1, 0, 2, 2), (0, 1, 1, 2)]:
+            sub = img[y0::dy, x0::dx]
+            if sub.size:
+                raw += b"".join(b"\0" + r.tobytes() for r in sub)
+        _check_against_cv2(cli, tmp_path, _png(shp[1], shp[0], 8, 2, raw, interlace=1), ("adam7", shp))
+    ok, b = cv2.imencode(".bmp", rng.integers(0, 256, (13, 7, 3), dtype=np.uint8))
+    _check_against_cv2(cli, tmp_path, b.tobytes(), "bmp")
+
+
+def test_corrupt_files_fail_loudly(cli, tmp_path):
+    for name, data in [("trunc.jpg", open(os.path.join(GOLD, "a_420_q90.jpg"), "rb").read()[:200]), ("junk.png", b"\x89PNG\r\n\x1a\n" + b"\0" * 40),
+                       ("empty.jpg", b""), ("text.jpg", b"hello")]:
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        got, msg = decode(cli, p, str(tmp_path / "o.pnm"), False)
+        assert got is None and "error" in msg, name
+
+
+def test_yaml_matches_opencv_filestorage(cli, tmp_path):
+    """Everything cv::FileStorage writes into the kinds of files the reference reads (scalars, quoted strings, string lists,
+    matrices of every depth incl. multi-line data and multi-channel dt, a nested mapping) comes back identical."""
+    cv2 = pytest.importorskip("cv2")
+    p = str(tmp_path / "t.yml")
+    mats = {"camID": np.array([[0, 1], [2, 3], [4, 5], [7, 6]], np.int32),
+            "K": np.array([[1234.56789012345, 0, 1e-300], [0, -2.5e10, 3], [1 / 3, np.pi * 1e5, 1]]),
+            "Kf": (np.arange(40, dtype=np.float32).reshape(4, 10) / 7),
+            "u8": np.arange(12, dtype=np.uint8).reshape(3, 4),
+            "s16": np.array([[-10000, 5, 32767]], np.int16),
+            "c3": np.arange(24, dtype=np.uint8).reshape(2, 4, 3)}
+    fs = cv2.FileStorage(p, cv2.FILE_STORAGE_WRITE)
+    fs.write("filepath", "D:/data set/x/")
+    fs.write("PyrmNum", 4)
+    fs.write("ws", 0.5)
+    fs.write("neg", -3)
+    fs.write("name with colon", "a: b")
+    for k, m in mats.items():
+        fs.write(k, m)
+    fs.write("imagelist", ["0001_Cam0.jpg", "0001 Cam1.jpg", "x,y.jpg"])
+    fs.startWriteStruct("map", cv2.FileNode_MAP)
+    fs.write("a", 1)
+    fs.write("b", "s")
+    fs.endWriteStruct()
+    fs.write("after", 7)
+    fs.release()
+    d = json.loads(subprocess.run([cli, "--dump-yaml", p], check=True, capture_output=True, text=True).stdout)
+    assert list(d)[:5] == ["filepath", "PyrmNum", "ws", "neg", "name with colon"] and list(d)[-1] == "after"
+    assert d["filepath"] == "D:/data set/x/" and d["PyrmNum"] == "4" and d["ws"] == "0.5" and d["neg"] == "-3" and d["name with colon"] == "a: b"
+    assert d["imagelist"] == ["0001_Cam0.jpg", "0001 Cam1.jpg", "x,y.jpg"]
+    assert d["map"] == {"a": "1", "b": "s"} and d["after"] == "7"
+    rd = cv2.FileStorage(p, cv2.FILE_STORAGE_READ)
+    for k, m in mats.items():
+        ours = np.array([struct.unpack(">d", bytes.fromhex(h))[0] for h in d[k]["hex"]])
+        ref = rd.getNode(k).mat()
+        assert (d[k]["rows"], d[k]["cols"], d[k]["channels"]) == (m.shape[0], m.shape[1], m.shape[2] if m.ndim == 3 else 1)
+        assert np.array_equal(ours.astype(m.dtype).reshape(m.shape), ref.reshape(m.shape)), k  # what OpenCV reads back
+        assert np.array_equal(ours.astype(m.dtype).reshape(m.shape), m), k                       # = what was written
+
+
+def test_yaml_edge_cases(cli, tmp_path):
+    p = str(tmp_path / "e.yml")
+    open(p, "wb").write(b"\xef\xbb\xbf%YAML:1.0\r\n---\r\n# comment\r\nisoutput: 1\r\nx: 1.2345678901234501e+003\r\ninf: .Inf\r\nninf: -.Inf\r\n"
+                        b"list: [ \"a b\", c,\r\n   \"d,e\" ]\r\nempty:\r\nblock:\r\n- p\r\n- \"q r\"\r\nM: !!opencv-matrix\r\n   rows: 1\r\n   cols: 2\r\n"
+                        b"   dt: d\r\n   data: [ .Nan,\r\n      -.Inf ]\r\n...\r\n")
+    d = json.loads(subprocess.run([cli, "--dump-yaml", p], check=True, capture_output=True, text=True).stdout)
+    assert d["isoutput"] == "1" and d["x"] == "1.2345678901234501e+003" and d["list"] == ["a b", "c", "d,e"]
+    assert d["empty"] == [] and d["block"] == ["p", "q r"]
+    v = [struct.unpack(">d", bytes.fromhex(h))[0] for h in d["M"]["hex"]]
+    assert np.isnan(v[0]) and v[1] == -np.inf
+    bad = str(tmp_path / "bad.yml")
+    open(bad, "w").write("%YAML:1.0\nM: !!opencv-matrix\n   rows: 2\n   cols: 2\n   dt: d\n   data: [ 1., 2., 3. ]\n")
+    r = subprocess.run([cli, "--dump-yaml", bad], capture_output=True, text=True)
+    assert r.returncode != 0 and "rows*cols does not match data" in r.stdout

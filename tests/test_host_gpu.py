@@ -64,3 +64,36 @@ def test_cli_native_rectify(tmp_path, golden_dir):
     assert len(xyz) == n and n > 0
     assert np.array_equal(xyz.view(np.int32), pxyz.astype(np.float32).view(np.int32))
     assert np.array_equal(bgr, pbgr)
+
+
+@pytest.mark.parametrize("fmt", ["jpg", "png"])
+def test_cli_reads_the_references_image_formats(tmp_path, golden_dir, fmt):
+    """The reference's data sets are JPEG frames and JPEG masks read with cv::imread (BatchProcess/main.cpp:66,
+    CStereoMatching.cpp:147-151).  `reconstruction config.yml` on such a data set decodes them natively (sbimg.cpp); the cloud must
+    equal, bit for bit, the one obtained when OpenCV decodes the same files and the same C ABI calls are driven from Python."""
+    cv2 = pytest.importorskip("cv2")
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    g = np.load(os.path.join(golden_dir, "rectify_cv2.npz"))
+    c = "a"
+    L, (w0, h0) = int(g[c + "_pyrm_num"]), (int(v) for v in g[c + "_lowest"])
+    origin = tuple(int(v) for v in g[c + "_origin"])
+    cams = [(g[c + "_K0"], g[c + "_Rt0"]), (g[c + "_K1"], g[c + "_Rt1"])]
+    cfg = stage.write_raw_dataset(str(tmp_path), L, w0, h0, origin, cams, [g[c + "_src_image0"], g[c + "_src_image1"]],
+                                  [g[c + "_src_mask0"], g[c + "_src_mask1"]], [[0, 1]], isoutput=1, fmt=fmt)
+    r = subprocess.run([os.path.join(HOST, "reconstruction"), cfg], cwd=str(tmp_path), capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    xyz, bgr = stage.read_ply_f32(str(tmp_path / "cloud0.ply"))
+    st = capi.StereoB200(L, w0, h0, *origin)
+    cal = capi.rectify_calib(cams[0][0], cams[0][1], cams[1][0], cams[1][1], origin, w0, L)
+    for j in (0, 1):
+        img = cv2.imread(str(tmp_path / f"0001_Cam{j}.{fmt}"), cv2.IMREAD_COLOR)
+        msk = cv2.imread(str(tmp_path / "mask" / f"0001_Cam{j}.{fmt}"), cv2.IMREAD_GRAYSCALE)
+        st.rectify_view(j, img, msk, cams[j][0], cal["R_new"][j], cal["P_scaled"][j])
+    st.pair_build()
+    st.set_calib(cal["Q"], cal["R_final"], cal["T_final"])
+    n = st.match_pair()
+    pxyz, pbgr, _ = st.get_points(n)
+    assert len(xyz) == n and n > 0
+    assert np.array_equal(xyz.view(np.int32), pxyz.astype(np.float32).view(np.int32))
+    assert np.array_equal(bgr, pbgr)
