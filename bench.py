@@ -379,6 +379,27 @@ def run_ours(args):
         rectify = {"ms_per_pair": min(ts), "what": "sb200_rectify_view x2 + sb200_pair_build at the top size from pinned original frames "
                    "(H2D 100.7 MB inside), best of 3", "Mpix_per_s": 2 * npx / (min(ts) * 1e-3) / 1e6}
 
+    # the sink's per-pair filter (the step after the hot path) on the points of the last end-to-end pair, measured once
+    # per run outside the timed steps: H2D of the f64 points + outlier removal + normals + orientation; D2H of the records excluded
+    sink = None
+    if rank == 0 and n_pts_e2e > 0:
+        from reconstruction_b200 import stage as _stage
+
+        cams = _stage.rig_cameras(2, W, H)
+        center = -cams[0][1][:, :3].T @ cams[0][1][:, 3]
+        pts = pin_xyz[0][:n_pts_e2e].numpy()
+        best = None
+        for it in range(2):
+            t0 = time.perf_counter()
+            _rec, kept, st_ = capi.sink_filter(pts, 100, 1.0, 2.5, center, device=local)  # CReconstruction.cpp:19 parameters
+            wall = time.perf_counter() - t0
+            if best is None or st_["device_ms"] < best["device_ms"]:
+                best = {"points_in": int(n_pts_e2e), "points_kept": int(len(kept)), "device_ms": st_["device_ms"], "wall_ms": 1e3 * wall,
+                        "Mpts_per_s": n_pts_e2e / (st_["device_ms"] * 1e-3) / 1e6, "widened_queries": st_["widened_queries"],
+                        "what": "sb200_sink_filter (meanK 100, stddev x1, normal radius 2.5): float narrowing, two cell sorts, k-nearest mean "
+                                "distances by radix select, host mean/stddev, keep flags + scan, covariance normals; best of 2"}
+        sink = best
+
     # totals over ranks
     tot_pts = n_pts * NC
     tot_launch = launches
@@ -438,6 +459,7 @@ def run_ours(args):
                               "frac_of_hbm_peak": (12 * ncc_px * prof_steps / (ncc_ms * 1e-3) / 1e9 / peak) if ncc_ms > 0 else None,
                               "exact_fallback_pixels_per_step": int(counters[0]) // max(prof_steps, 1)},
             "rectify": rectify,
+            "sink_filter": sink,
             "stage_ms_per_step": {k: round(float(stage_ms[i]) / prof_steps, 4) for i, k in enumerate(
                 ["pyramid", "FindMargin", "InitialMatch", "Smooth", "Order", "Unique1", "Rematch", "Unique2", "Median", "Refine",
                  "Unique3", "ToCloud", "RefineSweepsOnly"])},

@@ -184,6 +184,20 @@ SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, int level, double* sweep_
  * flat windows, wide ranges), [1] = out-of-table pixel evaluations of the refinement kernel. */
 SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
 
+/* ---- the sink's per-pair filter, on the device (next row f-3) ---------------------------------------
+ * What CCloudOptimization::filter(idx) does to the points InsertPoint collected for one camera pair before it meshes them
+ * (CloudOptimization/CCloudOptimization.cpp:64-121): pcl::StatisticalOutlierRemoval (setMeanK / setStddevMulThresh, :79-83),
+ * pcl::NormalEstimationOMP with a radius search (:99-106) and the flip of every normal towards CamCenter[idx] (:109-116).
+ * Points are narrowed to float32 as InsertPoint does (:59-62).  PCL is not under /root/reference: parity is against
+ * oracle/sink_oracle.py.  xyz: n x 3 f64 in InsertPoint order (host).  Output: the kept points in their original
+ * order, 7 floats each (x y z normal_x normal_y normal_z curvature = the PointNormal fields savePLYFileBinary writes, :119),
+ * kept_index (optional): their indices in the input.  stats5 (optional): mean, stddev, threshold of the SOR distances, device
+ * milliseconds, number of queries whose search ring had to grow.  No CPU path: SB200_ERR_NO_DEVICE without a GPU. */
+SB200_API int sb200_sink_filter(int device, const double* xyz, int64_t n, int sor_meank, double sor_std_mul, double normal_radius,
+                                const double* cam_center, float* out_xyz_normal_curv, int32_t* kept_index, int64_t capacity,
+                                int64_t* n_kept, double* stats5);
+SB200_API const char* sb200_sink_last_error(void);
+
 /* glibc-compatible exp() used by the refinement weights (see DESIGN.md "exp"); host twin of the
  * device function, exported so the CPU tests can pin it against the C library. */
 SB200_API double sb200_exp_host(double x);

@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -37,7 +38,8 @@ STAGE_NAMES = {
 def build(kind: str | None = None) -> None:
     """Run the oracle Makefile (ref is skipped by make itself when /root/reference is absent)."""
     targets = ["port", "ref"] if kind is None else [kind]
-    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True)
+    # make's chatter goes to stderr: bench.py's stdout carries exactly one JSON line
+    subprocess.run(["make", "-s", "-C", HERE] + targets, check=True, stdout=sys.stderr)
 
 
 def available(kind: str) -> bool:

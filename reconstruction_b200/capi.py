@@ -33,6 +33,7 @@ SYMBOLS = [
     "sb200_exp_host",
     "sb200_rectify_calib", "sb200_stereo_rectify_host", "sb200_rectify_view", "sb200_pair_build", "sb200_get_rectify_maps",
     "sb200_set_rectify_maps", "sb200_get_remapped_mask",
+    "sb200_sink_filter", "sb200_sink_last_error",
 ]
 
 
@@ -100,6 +101,8 @@ def load():
         "sb200_get_rectify_maps": (i32, [vp, vp, vp]),
         "sb200_set_rectify_maps": (i32, [vp, vp, vp]),
         "sb200_get_remapped_mask": (i32, [vp, vp]),
+        "sb200_sink_filter": (i32, [i32, vp, i64, i32, dbl, dbl, vp, vp, vp, i64, P(i64), vp]),
+        "sb200_sink_last_error": (C.c_char_p, []),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -335,3 +338,22 @@ def stereo_rectify_host(K1, K2, size, R, T):
 
 def exp_host(x: float) -> float:
     return load().sb200_exp_host(float(x))
+
+
+def sink_filter(xyz, sor_meank, sor_std_mul, normal_radius, cam_center, device=0):
+    """CCloudOptimization::filter's point processing on the GPU (sb200_sink_filter): returns (records [m,7] f32 =
+    x y z nx ny nz curvature of the kept points in input order, kept_index [m] i32, stats dict)."""
+    xyz = np.ascontiguousarray(xyz, np.float64)
+    n = xyz.shape[0]
+    out = np.empty((n, 7), np.float32)
+    kept = np.empty(n, np.int32)
+    cam = np.ascontiguousarray(cam_center, np.float64)
+    m = C.c_int64()
+    stats = np.zeros(5)
+    lib = load()
+    rc = lib.sb200_sink_filter(device, _p(xyz), n, int(sor_meank), float(sor_std_mul), float(normal_radius), _p(cam), _p(out), _p(kept), n,
+                               C.byref(m), _p(stats))
+    if rc != 0:
+        raise StereoError(f"sink_filter: {lib.sb200_status_string(rc).decode()} - {lib.sb200_sink_last_error().decode()}")
+    return out[:m.value].copy(), kept[:m.value].copy(), {"mean": stats[0], "stddev": stats[1], "threshold": stats[2], "device_ms": stats[3],
+                                                        "widened_queries": int(stats[4])}

@@ -1,6 +1,10 @@
 #include "CCloudOptimization.h"
 
 #include <stdio.h>
+#include <stdlib.h>
+#include <sys/stat.h>
+
+#include "../../include/stereo_b200.h"
 
 void CCloudOptimization::Init(int sor_meank, double sor_stdThres, int sor_meank1, double sor_stdThres1, double mls_radius,
                               CManageData* m_data, bool isdelete_) {
@@ -15,7 +19,11 @@ void CCloudOptimization::Init(int sor_meank, double sor_stdThres, int sor_meank1
   bgr.clear();
   pair_begin.assign(1, 0);
   pair_index.clear();
+  normals.clear();
+  kept_per_pair.clear();
   open_begin_ = 0;
+  if (const char* e = getenv("SB200_SINK")) sink_enabled = atoi(e) != 0;
+  mkdir("tmp", 0777);  // "mkdir tmp" (:55-57)
 }
 
 void CCloudOptimization::InsertPoint(sbcv::Mat p) {
@@ -32,9 +40,44 @@ void CCloudOptimization::InsertPoints(const double* p, const unsigned char* c, s
 }
 
 void CCloudOptimization::filter(int idx) {
+  const size_t begin = open_begin_, end = xyz.size() / 3;
   pair_index.push_back(idx);
-  open_begin_ = xyz.size() / 3;
+  open_begin_ = end;
   pair_begin.push_back(open_begin_);
+  if (!sink_enabled || end <= begin) { kept_per_pair.push_back(0); return; }
+  printf("Initial points: %zu\n", end - begin);
+  // CamCenter[idx] = centre of the pair's first camera (:50-51)
+  double cam[3] = {0, 0, 0};
+  if (m_ImageData && idx >= 0 && idx < (int)m_ImageData->cam.size() && !m_ImageData->cam[idx][0].CamCenter.empty())
+    for (int k = 0; k < 3; k++) cam[k] = m_ImageData->cam[idx][0].CamCenter.at<double>(k, 0);
+  std::vector<float> rec(7 * (end - begin));
+  int64_t kept = 0;
+  double stats[5] = {0, 0, 0, 0, 0};
+  const int rc = sb200_sink_filter(sink_device, xyz.data() + 3 * begin, (int64_t)(end - begin), m_sor_meank, m_sor_stdThres, m_mls_radius, cam,
+                                   rec.data(), nullptr, (int64_t)(end - begin), &kept, stats);
+  if (rc != SB200_OK) {
+    last_status = rc;
+    last_error = std::string(sb200_status_string(rc)) + ": " + sb200_sink_last_error();
+    printf("sink filter of pair %d failed: %s\n", idx, last_error.c_str());
+    kept_per_pair.push_back(0);
+    return;
+  }
+  printf("Cloud after filtering: %lld points (mean distance %.6g, stddev %.6g, threshold %.6g; %.2f ms on the GPU)\n", (long long)kept, stats[0],
+         stats[1], stats[2], stats[3]);
+  normals.insert(normals.end(), rec.begin(), rec.begin() + 7 * kept);  // *cloud_normals += *cloud_normal (:117)
+  kept_per_pair.push_back((size_t)kept);
+  WritePlyPointNormal("tmp/cloud_filter.ply", rec.data(), (size_t)kept);  // :119 (the mesher's input)
+}
+
+bool WritePlyPointNormal(const std::string& path, const float* rec7, size_t n) {
+  FILE* fp = fopen(path.c_str(), "wb");
+  if (!fp) return false;
+  fprintf(fp, "ply\nformat binary_little_endian 1.0\ncomment PCL generated\nelement vertex %zu\n", n);
+  fprintf(fp, "property float x\nproperty float y\nproperty float z\nproperty float normal_x\nproperty float normal_y\nproperty float normal_z\n"
+              "property float curvature\nend_header\n");
+  const bool ok = n == 0 || fwrite(rec7, 28, n, fp) == n;
+  fclose(fp);
+  return ok;
 }
 
 bool WritePlyF32(const std::string& path, const double* xyz, const unsigned char* bgr, size_t n) {
@@ -68,4 +111,9 @@ void CCloudOptimization::run() {
     printf("wrote %zu points of %zu pairs to %s\n", n, pair_index.size(), m_ImageData->outfilename.c_str());
   else
     printf("cannot write %s\n", m_ImageData->outfilename.c_str());
+  if (!normals.empty()) {
+    const std::string path = m_ImageData->outfilename + ".normals.ply";
+    if (WritePlyPointNormal(path, normals.data(), normals.size() / 7)) printf("wrote %zu oriented points to %s\n", normals.size() / 7, path.c_str());
+    else printf("cannot write %s\n", path.c_str());
+  }
 }
