@@ -48,6 +48,28 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """Everything any library prints to fd 1 (NCCL's version banner, make's chatter) goes to stderr: stdout carries exactly one
+    JSON line, written by emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, line)
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 # ------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
@@ -157,7 +179,7 @@ def run_reference(args):
         if px / est_rate <= budget:
             w0, h0 = cand
             break
-    r = cpu_run(kind, L, w0, h0, args.steps, args.warmup)
+    r = cpu_run(kind, L, w0, h0, args.steps, args.warmup, threads=ncpu)  # explicit: torchrun exports OMP_NUM_THREADS=1
     out = {
         "impl": "reference", "metric": METRIC, "value": r["mpix_s"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -167,7 +189,7 @@ def run_reference(args):
         "cpu_baseline": {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"]},
         "e2e": {"value": r["mpix_s"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
     return 0
 
 
@@ -219,30 +241,22 @@ def run_ours(args):
     pin_xyz = [torch.empty((npx, 3), dtype=torch.float64).pin_memory() for _ in range(NC)]
     torch.cuda.synchronize()
 
-    exchangers = [xchg.PointExchanger() for _ in range(NC)] if world > 1 else None
-    # NCCL collectives must be issued in the same order on every rank: the contexts of a rank take turns
-    # (step 0 ctx 0, step 0 ctx 1, step 1 ctx 0, ...) through this ticket
-    turn = threading.Condition()
-    ticket = [0]
+    # N > 1: the rank's contexts only snapshot their points; one exchange thread per rank issues the NCCL all-gathers in ticket
+    # order (reconstruction_b200/exchange.py::OrderedPointExchange), so no context ever waits for another rank
+    exchange_on = [world > 1]
+    xch = [None]
     aborted = []
 
     def exchange(k, seq, n_local):
-        """All-gather of the per-pair point buffers over NCCL, overlapped with the next pair's matching
-        (reconstruction_b200/exchange.py::PointExchanger); the last ones are waited for inside the timed region."""
-        if world == 1 or exchangers is None:
+        """All-gather of the per-pair point buffers over NCCL, overlapped with the following pairs' matching; the last ones are
+        waited for inside the timed region."""
+        if xch[0] is None:
             return
-        with turn:
-            while ticket[0] != seq * NC + k:
-                if aborted:
-                    raise RuntimeError("another context of this rank failed")
-                turn.wait(timeout=1.0)
-            xp, bp, pp, _ = gs[k].points_device()
-            xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
-            bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
-            pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
-            exchangers[k].submit(xyz, bgr, pix, n_local)
-            ticket[0] += 1
-            turn.notify_all()
+        xp, bp, pp, _ = gs[k].points_device()
+        xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
+        bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
+        pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
+        xch[0].submit(k, seq, xyz, bgr, pix, n_local)
 
     def step_resident(k, i):
         sp = pairs[(i + k) % 2]
@@ -274,7 +288,7 @@ def run_ours(args):
                 gs[k].stage_ms(reset=True)
                 gs[k].refine_profile(reset=True)
         launches0 = sum(gs[k].launch_count() for k in ctxs)
-        ticket[0] = 0
+        xch[0] = xchg.OrderedPointExchange(len(ctxs), steps * len(ctxs)) if (exchange_on[0] and len(ctxs) == NC) else None
         npts = [0] * NC
         errs = []
 
@@ -286,8 +300,8 @@ def run_ours(args):
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
                 aborted.append(k)
-                with turn:
-                    turn.notify_all()
+                if xch[0] is not None:
+                    xch[0].abort(e)
 
         barrier()
         lead = streams[ctxs[0]]
@@ -303,9 +317,8 @@ def run_ours(args):
         if errs:
             raise errs[0]
         with torch.cuda.stream(lead):
-            if exchangers is not None:
-                for k in ctxs:
-                    exchangers[k].finish()  # the last steps' gathers complete inside the timed region
+            if xch[0] is not None:
+                xch[0].finish()  # the last steps' gathers complete inside the timed region
             for k in ctxs[1:]:
                 lead.wait_stream(streams[k])
             ev1.record(lead)
@@ -327,12 +340,11 @@ def run_ours(args):
 
     # (1) one pair at a time on context 0, with the per-stage / per-launch timers on: the roofline and stage figures
     g = gs[0]
-    saved_world_exchange = exchangers
     single_ms, n_pts, single_launches = None, 0, 0
     if NC > 1:
-        exchangers = None  # the single-context pass times the matcher alone
-        single_ms, n_pts, single_launches = timed(step_resident, args.steps, [0], profile=True)
-        exchangers = saved_world_exchange
+        single_ms, n_pts, single_launches = timed(step_resident, args.steps, [0], profile=True)  # the matcher alone, no exchange
+    if world > 1:
+        timed(step_resident, 1, every)  # untimed: the exchange's staging and gather buffers get allocated here
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -400,6 +412,25 @@ def run_ours(args):
                                 "distances by radix select, host mean/stddev, keep flags + scan, covariance normals; best of 2"}
         sink = best
 
+    # native JPEG decode of one frame of the named size (the data format in front of the path): host, one thread
+    decode = None
+    if rank == 0:
+        try:
+            import cv2
+            import tempfile
+
+            host_bin = os.path.join(ROOT, "reconstruction_b200", "host", "reconstruction")
+            ok, jb = cv2.imencode(".jpg", pairs[0].image[0], [cv2.IMWRITE_JPEG_QUALITY, 95])
+            if ok and os.path.exists(host_bin):
+                with tempfile.NamedTemporaryFile(suffix=".jpg") as tf:
+                    tf.write(jb.tobytes())
+                    tf.flush()
+                    r = subprocess.run([host_bin, "--decode-bench", tf.name, "3"], capture_output=True, text=True, timeout=120)
+                    decode = json.loads(r.stdout)
+                    decode["what"] = "sbcv::imdecode (baseline JPEG, quality 95, 4:2:0) of one top-size frame, one host thread, best of 3"
+        except Exception as e:  # noqa: BLE001
+            decode = {"unavailable": str(e)[:200]}
+
     # totals over ranks
     tot_pts = n_pts * NC
     tot_launch = launches
@@ -460,6 +491,7 @@ def run_ours(args):
                               "exact_fallback_pixels_per_step": int(counters[0]) // max(prof_steps, 1)},
             "rectify": rectify,
             "sink_filter": sink,
+            "jpeg_decode": decode,
             "stage_ms_per_step": {k: round(float(stage_ms[i]) / prof_steps, 4) for i, k in enumerate(
                 ["pyramid", "FindMargin", "InitialMatch", "Smooth", "Order", "Unique1", "Rematch", "Unique2", "Median", "Refine",
                  "Unique3", "ToCloud", "RefineSweepsOnly"])},
@@ -469,10 +501,10 @@ def run_ours(args):
             kind, label = pick_cpu_kind()
             ncpu = os.cpu_count() or 8
             w0c, h0c = (64, 48) if ncpu < 16 else (96, 72)  # ~10-30 s of CPU work
-            r = cpu_run(kind, L, w0c, h0c, 1, 0)
+            r = cpu_run(kind, L, w0c, h0c, 1, 0, threads=ncpu)
             out["cpu_baseline"] = {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"],
                                    "sec": r["sec_per_step"]}
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -490,6 +522,7 @@ def main():
     ap.add_argument("--pairs-in-flight", type=int, default=3, help="camera pairs matched concurrently per GPU (contexts per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    protect_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -109,7 +109,7 @@ __device__ __forceinline__ void row_ranges(const Grid& g, const unsigned* __rest
   lo = lower_bound(keys, n, cell_id(g, max(cx - R, 0), y, z));
   hi = lower_bound(keys, n, cell_id(g, min(cx + R, g.nx - 1), y, z) + 1u);
 }
-// `f(valid, p)` is called by all 32 lanes together (warp-uniform loop), `valid` lanes holding one candidate each.  For R == 1
+// `f(valid, j, p)` is called by all 32 lanes together (warp-uniform loop), `valid` lanes holding one candidate each.  For R == 1
 // (9 rows) the caller passes the runs it looked up once (clo, chi); wider rings look their rows up again in every sweep
 // (rare: isolated points).
 template <class F>
@@ -125,10 +125,20 @@ __device__ __forceinline__ void sweep_block(const Grid& g, const unsigned* __res
       for (unsigned j0 = a; j0 < b; j0 += 32) {
         const unsigned j = j0 + lane;
         const bool valid = j < b;
-        f(valid, sp[valid ? j : a]);
+        f(valid, valid ? j : a, sp[valid ? j : a]);
       }
     }
   }
+}
+
+#define SINK_KEY_CAP 1024  // candidate distances a warp keeps in shared memory between the passes of its radix select
+
+// adds one digit of `key` to the per-warp histogram; lanes with the same digit elect one lane (neighbours share their leading
+// digits: no same-address atomics).  Called by all 32 lanes.
+__device__ __forceinline__ void hist_add(int* hist, bool take, unsigned key, int shift) {
+  const unsigned bin = take ? ((key >> shift) & 255u) : 256u;
+  const unsigned peers = __match_any_sync(0xffffffffu, bin);
+  if (bin < 256u && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
 }
 
 struct HistPass {
@@ -137,19 +147,23 @@ struct HistPass {
   int shift;
   bool first;
   int* hist;
-  __device__ __forceinline__ void operator()(bool valid, const float4& p) {
+  unsigned* skeys;  // first pass: the candidates' distance bit patterns are kept here (up to SINK_KEY_CAP)
+  int cnt;
+  __device__ __forceinline__ void operator()(bool valid, unsigned, const float4& p) {
     const unsigned key = __float_as_uint(dist2(p.x, p.y, p.z, qx, qy, qz));
-    // neighbours share their leading digits: lanes with the same bin elect one to add their count (no same-address atomics)
-    const unsigned bin = (valid && (first || (key >> (shift + 8)) == prefix)) ? ((key >> shift) & 255u) : 256u;
-    const unsigned peers = __match_any_sync(0xffffffffu, bin);
-    if (bin < 256u && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+    if (first) {
+      const int nv = __popc(__ballot_sync(0xffffffffu, valid));  // valid lanes are a prefix of the warp
+      if (valid && cnt + nv <= SINK_KEY_CAP) skeys[cnt + (threadIdx.x & 31)] = key;
+      cnt += nv;
+    }
+    hist_add(hist, valid && (first || (key >> (shift + 8)) == prefix), key, shift);
   }
 };
 struct SumPass {
   float qx, qy, qz;
   unsigned T;
   double sum;
-  __device__ __forceinline__ void operator()(bool valid, const float4& p) {
+  __device__ __forceinline__ void operator()(bool valid, unsigned, const float4& p) {
     const float d2 = dist2(p.x, p.y, p.z, qx, qy, qz);
     if (valid && __float_as_uint(d2) < T) sum += (double)__fsqrt_rn(d2);
   }
@@ -159,8 +173,10 @@ struct SumPass {
 __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* __restrict__ keys, const float4* __restrict__ sp, unsigned n_valid,
                                                        int mean_k, double* __restrict__ mean_dist, unsigned long long* __restrict__ counters) {
   __shared__ int s_hist[8][256];
+  __shared__ unsigned s_keys[8][SINK_KEY_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int* hist = s_hist[warp];
+  unsigned* skeys = s_keys[warp];
   const unsigned nwarps = gridDim.x * 8;
   const int rmax = max(g.nx, max(g.ny, g.nz));
   for (unsigned j = blockIdx.x * 8 + warp; j < n_valid; j += nwarps) {
@@ -172,13 +188,22 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
     row_ranges(g, keys, n_valid, cx, cy, cz, 1, 0, lane, clo, chi);
     for (int R = 1;;) {
       unsigned prefix = 0;
-      int rank = want - 1, less = 0, total = 0;
+      int rank = want - 1, less = 0, total = 0, staged = -1;  // staged >= 0: that many keys sit in shared memory
       bool enough = true;
       for (int pass = 0; pass < 4 && enough; pass++) {
         for (int b = lane; b < 256; b += 32) hist[b] = 0;
         __syncwarp();
-        HistPass hp{q.x, q.y, q.z, prefix, 24 - 8 * pass, pass == 0, hist};
-        sweep_block(g, keys, sp, n_valid, cx, cy, cz, R, lane, clo, chi, hp);
+        if (staged >= 0) {  // later passes read the staged distances instead of the points
+          for (int i0 = 0; i0 < staged; i0 += 32) {
+            const int i = i0 + lane;
+            const unsigned key = i < staged ? skeys[i] : 0u;
+            hist_add(hist, i < staged && (key >> (32 - 8 * pass)) == prefix, key, 24 - 8 * pass);
+          }
+        } else {
+          HistPass hp{q.x, q.y, q.z, prefix, 24 - 8 * pass, pass == 0, hist, skeys, 0};
+          sweep_block(g, keys, sp, n_valid, cx, cy, cz, R, lane, clo, chi, hp);
+          if (pass == 0 && hp.cnt <= SINK_KEY_CAP) staged = hp.cnt;
+        }
         __syncwarp();
         int s = 0;
         int h[8];
@@ -220,9 +245,17 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
         R = min(max(R + 1, (int)ceilf(__fsqrt_ru(__uint_as_float(T)) / (g.c * 0.99999f))), rmax);
         continue;
       }
-      SumPass spass{q.x, q.y, q.z, T, 0.0};
-      sweep_block(g, keys, sp, n_valid, cx, cy, cz, R, lane, clo, chi, spass);
-      double s = spass.sum;
+      double s = 0;
+      if (staged >= 0) {
+        for (int i = lane; i < staged; i += 32) {
+          const unsigned key = skeys[i];
+          if (key < T) s += (double)__fsqrt_rn(__uint_as_float(key));
+        }
+      } else {
+        SumPass spass{q.x, q.y, q.z, T, 0.0};
+        sweep_block(g, keys, sp, n_valid, cx, cy, cz, R, lane, clo, chi, spass);
+        s = spass.sum;
+      }
 #pragma unroll
       for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
       if (enough) s += (double)(want - less) * (double)__fsqrt_rn(__uint_as_float(T));
@@ -241,11 +274,11 @@ __global__ void k_keep_flags(const double* __restrict__ mean_dist, const float4*
 
 struct CovPass {
   float qx, qy, qz, r2;
-  const int* keep;
+  const unsigned char* keep;  // keep flags in the order of the sorted array
   double s[9];
   int cnt;
-  __device__ __forceinline__ void operator()(bool valid, const float4& p) {
-    if (!valid || !keep[__float_as_int(p.w)]) return;
+  __device__ __forceinline__ void operator()(bool valid, unsigned j, const float4& p) {
+    if (!valid || !keep[j]) return;
     if (!(dist2(p.x, p.y, p.z, qx, qy, qz) < r2)) return;
     const double dx = (double)p.x - (double)qx, dy = (double)p.y - (double)qy, dz = (double)p.z - (double)qz;  // exact
     s[0] += dx; s[1] += dy; s[2] += dz;
@@ -292,38 +325,60 @@ __device__ void smallest_eigen(double a[3][3], double& lambda, double v[3], doub
   for (int k = 0; k < 3; k++) v[k] = V[k][m] / nrm;
 }
 
-__global__ void __launch_bounds__(256) k_normals(Grid g, const unsigned* __restrict__ keys, const float4* __restrict__ sp, unsigned n_valid, const int* __restrict__ keep,
-                                                 const int* __restrict__ rank, float radius2, float cx_, float cy_, float cz_, float* __restrict__ out,
+__global__ void k_keep_sorted(const float4* __restrict__ sp, unsigned n_valid, const int* __restrict__ keep, unsigned char* __restrict__ keep_s) {
+  const unsigned j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n_valid) keep_s[j] = (unsigned char)keep[__float_as_int(sp[j].w)];
+}
+
+// A warp takes 32 consecutive queries of the sorted array: the neighbourhood sums of query b are gathered by all lanes together
+// and handed to lane b; then the 32 lanes solve their 32 eigenproblems side by side (a lane-0-only solve left 31 lanes idle
+// for the longest part of the kernel: 46 -> see DESIGN.md 11).
+__global__ void __launch_bounds__(256) k_normals(Grid g, const unsigned* __restrict__ keys, const float4* __restrict__ sp, unsigned n_valid,
+                                                 const unsigned char* __restrict__ keep, const int* __restrict__ rank, float radius2, float cx_, float cy_, float cz_, float* __restrict__ out,
                                                  int* __restrict__ kept_index) {
   const int lane = threadIdx.x & 31;
   const unsigned nwarps = gridDim.x * 8;
-  for (unsigned j = blockIdx.x * 8 + (threadIdx.x >> 5); j < n_valid; j += nwarps) {
-    const float4 q = sp[j];
-    const int orig = __float_as_int(q.w);
-    if (!keep[orig]) continue;
-    const int cx = cell_coord(q.x, g.minx, g.inv_c, g.nx), cy = cell_coord(q.y, g.miny, g.inv_c, g.ny), cz = cell_coord(q.z, g.minz, g.inv_c, g.nz);
-    CovPass cp{q.x, q.y, q.z, radius2, keep, {0, 0, 0, 0, 0, 0, 0, 0, 0}, 0};
-    unsigned clo, chi;
-    row_ranges(g, keys, n_valid, cx, cy, cz, 1, 0, lane, clo, chi);
-    sweep_block(g, keys, sp, n_valid, cx, cy, cz, 1, lane, clo, chi, cp);
+  for (unsigned base = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 32u; base < n_valid; base += nwarps * 32u) {
+    double ms[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // this lane's query: sums about the query point
+    int mcnt = -1;                                // -1: no query (past the end or not kept)
+    float4 mq = make_float4(0, 0, 0, 0);
+    const int nq = (int)min(32u, n_valid - base);
+    for (int b = 0; b < nq; b++) {
+      const unsigned j = base + b;
+      if (!keep[j]) continue;  // warp-uniform
+      const float4 q = sp[j];
+      const int cx = cell_coord(q.x, g.minx, g.inv_c, g.nx), cy = cell_coord(q.y, g.miny, g.inv_c, g.ny), cz = cell_coord(q.z, g.minz, g.inv_c, g.nz);
+      CovPass cp{q.x, q.y, q.z, radius2, keep, {0, 0, 0, 0, 0, 0, 0, 0, 0}, 0};
+      unsigned clo, chi;
+      row_ranges(g, keys, n_valid, cx, cy, cz, 1, 0, lane, clo, chi);
+      sweep_block(g, keys, sp, n_valid, cx, cy, cz, 1, lane, clo, chi, cp);
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+      for (int o = 16; o; o >>= 1) {
 #pragma unroll
-      for (int k = 0; k < 9; k++) cp.s[k] += __shfl_xor_sync(0xffffffffu, cp.s[k], o);
-      cp.cnt += __shfl_xor_sync(0xffffffffu, cp.cnt, o);
+        for (int k = 0; k < 9; k++) cp.s[k] += __shfl_xor_sync(0xffffffffu, cp.s[k], o);
+        cp.cnt += __shfl_xor_sync(0xffffffffu, cp.cnt, o);
+      }
+      if (lane == b) {
+#pragma unroll
+        for (int k = 0; k < 9; k++) ms[k] = cp.s[k];
+        mcnt = cp.cnt;
+        mq = q;
+      }
     }
-    if (lane != 0) continue;
+    if (mcnt < 0) continue;
+    const float4 q = mq;
+    const int orig = __float_as_int(q.w);
     float* o = out + (size_t)rank[orig] * 7;
     if (kept_index) kept_index[rank[orig]] = orig;
     o[0] = q.x; o[1] = q.y; o[2] = q.z;
-    if (cp.cnt < 3) {  // computePointNormal fails: NaN normal and curvature
+    if (mcnt < 3) {  // computePointNormal fails: NaN normal and curvature
       o[3] = o[4] = o[5] = o[6] = __int_as_float(0x7fc00000);
       continue;
     }
-    const double n = cp.cnt, mx = cp.s[0] / n, my = cp.s[1] / n, mz = cp.s[2] / n;
+    const double n = mcnt, mx = ms[0] / n, my = ms[1] / n, mz = ms[2] / n;
     double a[3][3];
-    a[0][0] = cp.s[3] / n - mx * mx; a[0][1] = a[1][0] = cp.s[4] / n - mx * my; a[0][2] = a[2][0] = cp.s[5] / n - mx * mz;
-    a[1][1] = cp.s[6] / n - my * my; a[1][2] = a[2][1] = cp.s[7] / n - my * mz; a[2][2] = cp.s[8] / n - mz * mz;
+    a[0][0] = ms[3] / n - mx * mx; a[0][1] = a[1][0] = ms[4] / n - mx * my; a[0][2] = a[2][0] = ms[5] / n - mx * mz;
+    a[1][1] = ms[6] / n - my * my; a[1][2] = a[2][1] = ms[7] / n - my * mz; a[2][2] = ms[8] / n - mz * mz;
     double lam, v[3], tr;
     smallest_eigen(a, lam, v, tr);
     float nx = (float)v[0], ny = (float)v[1], nz = (float)v[2];
@@ -505,7 +560,10 @@ int sink_filter_device(const double* d_xyz, int64_t n, int mean_k, double std_mu
   SK(mem.alloc(&d_out, (size_t)total * 7));
   if (kept_host) SK(mem.alloc(&d_kept, (size_t)total));
   const float r2 = (float)(radius * radius);
-  k_normals<<<grid, 256, 0, st>>>(gn.g, gn.keys, gn.sp, n_valid, keep, rank, r2, (float)cam[0], (float)cam[1], (float)cam[2], d_out, d_kept);
+  unsigned char* keep_s = nullptr;
+  SK(mem.alloc(&keep_s, n));
+  k_keep_sorted<<<(n_valid + 255) / 256, 256, 0, st>>>(gn.sp, n_valid, keep, keep_s);
+  k_normals<<<grid, 256, 0, st>>>(gn.g, gn.keys, gn.sp, n_valid, keep_s, rank, r2, (float)cam[0], (float)cam[1], (float)cam[2], d_out, d_kept);
   SK(cudaGetLastError());
   SK(cudaEventRecord(ev1, st));
   SK(cudaMemcpyAsync(out_host, d_out, sizeof(float) * 7 * (size_t)total, cudaMemcpyDeviceToHost, st));

@@ -6,6 +6,8 @@ process per GPU), gloo for the CPU tests.
 """
 from __future__ import annotations
 
+import threading
+
 import torch
 import torch.distributed as dist
 
@@ -94,6 +96,130 @@ class PointExchanger:
         if self.cnts is None:
             return None
         return self.cnts, self.out["xyz"], self.out["bgr"], self.out["pix"]
+
+
+class OrderedPointExchange:
+    """The exchange when a rank has several camera pairs in flight (one producer thread per context).
+
+    Collectives must be issued in the same order on every rank, and a producer must never wait for another rank.  So the
+    producers only SNAPSHOT: `submit(k, seq, ...)` copies the pair's points into one of this producer's staging slots on the
+    producer's own stream and returns; one exchange thread per rank issues the gathers in ticket order
+    (ticket = seq * n_producers + k, identical on every rank): it makes its stream wait for the snapshot, all-gathers the
+    counts (the only host-blocking step, and it blocks this thread alone), then all-gathers the payload padded to the largest
+    count.  A staging slot is reused once the gather that read it has been enqueued (host handshake) and has completed
+    (stream-level event wait), so a producer runs up to `slots` pairs ahead of the exchange.  `on_gathered(ticket, counts,
+    xyz_all, bgr_all, pix_all)` (optional) runs on the exchange thread after each gather has been enqueued."""
+
+    def __init__(self, n_producers, n_tickets, group=None, slots=2, on_gathered=None):
+        self.np_, self.n_tickets, self.group, self.slots, self.on_gathered = n_producers, n_tickets, group, slots, on_gathered
+        self.stage = {}
+        self.slot_free = {(k, s): threading.Event() for k in range(n_producers) for s in range(slots)}
+        for e in self.slot_free.values():
+            e.set()
+        self.slot_event = {}
+        self.queue = {}
+        self.cv = threading.Condition()
+        self.out = {}
+        self.err = None
+        self.last = None
+        self.xstream = None
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.started = False
+
+    def submit(self, k, seq, xyz, bgr, pix, n_local):
+        """Producer side; call with the producer's stream current.  Returns as soon as the snapshot copy is enqueued."""
+        slot = seq % self.slots
+        while not self.slot_free[(k, slot)].wait(timeout=1.0):
+            if self.err is not None:
+                raise RuntimeError("point exchange failed") from self.err
+        self.slot_free[(k, slot)].clear()
+        cuda = xyz.is_cuda
+        if cuda and (k, slot) in self.slot_event:
+            torch.cuda.current_stream(xyz.device).wait_event(self.slot_event[(k, slot)])  # the gather that read this slot is done
+        st = self.stage.get((k, slot))
+        if st is None:
+            st = {"xyz": torch.empty_like(xyz), "bgr": torch.empty_like(bgr), "pix": torch.empty_like(pix)}
+            self.stage[(k, slot)] = st
+        for name, t in (("xyz", xyz), ("bgr", bgr), ("pix", pix)):
+            st[name][:n_local].copy_(t[:n_local], non_blocking=True)
+        ev = None
+        if cuda:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(xyz.device))
+        with self.cv:
+            self.queue[seq * self.np_ + k] = (k, slot, int(n_local), ev, xyz.device)
+            if not self.started:
+                self.started = True
+                self.thread.start()
+            self.cv.notify_all()
+
+    def _gather_one(self, ticket, k, slot, n_local, ev, device):
+        world = dist.get_world_size(self.group)
+        st = self.stage[(k, slot)]
+        if ev is not None:
+            torch.cuda.current_stream(device).wait_event(ev)
+        cnts = allgather_counts(n_local, device, self.group).cpu()
+        nmax = max(int(cnts.max()), 1)
+        if st["xyz"].shape[0] < nmax:
+            raise ValueError(f"point buffers hold {st['xyz'].shape[0]} rows but another rank produced {nmax}")
+        res = {}
+        for name in ("xyz", "bgr", "pix"):
+            src = st[name][:nmax]
+            row = src[0].numel() if src.dim() > 1 else 1
+            buf = self.out.get(name)
+            need = world * st[name].shape[0] * row
+            if buf is None or buf.numel() < need:
+                buf = torch.empty(need, dtype=src.dtype, device=src.device)  # sized for the capacity once: no reallocation later
+                self.out[name] = buf
+            dst = buf[: world * nmax * row]
+            dist.all_gather_into_tensor(dst, src.reshape(-1), group=self.group)
+            res[name] = dst.view((world, nmax) + tuple(src.shape[1:]))
+        if ev is not None:
+            e2 = torch.cuda.Event()
+            e2.record(torch.cuda.current_stream(device))
+            self.slot_event[(k, slot)] = e2
+        self.last = (cnts, res["xyz"], res["bgr"], res["pix"])
+        if self.on_gathered is not None:
+            self.on_gathered(ticket, *self.last)
+        self.slot_free[(k, slot)].set()
+
+    def _run(self):
+        try:
+            for ticket in range(self.n_tickets):
+                with self.cv:
+                    while ticket not in self.queue:
+                        self.cv.wait(timeout=1.0)
+                        if self.err is not None:
+                            return
+                    k, slot, n_local, ev, device = self.queue.pop(ticket)
+                if device.type == "cuda":
+                    if self.xstream is None:
+                        self.xstream = torch.cuda.Stream(device=device)
+                    with torch.cuda.stream(self.xstream):
+                        self._gather_one(ticket, k, slot, n_local, ev, device)
+                else:
+                    self._gather_one(ticket, k, slot, n_local, ev, device)
+        except BaseException as e:  # noqa: BLE001
+            self.err = e
+            for ev in self.slot_free.values():
+                ev.set()
+
+    def abort(self, exc):
+        self.err = exc
+        with self.cv:
+            self.cv.notify_all()
+
+    def finish(self):
+        """Wait until every ticket has been gathered (the current CUDA stream then waits for the last gather); returns the last
+        gathered buffers."""
+        if self.started:
+            while self.thread.is_alive():
+                self.thread.join(timeout=1.0)
+        if self.err is not None:
+            raise RuntimeError("point exchange failed") from self.err
+        if self.xstream is not None:
+            torch.cuda.current_stream(self.xstream.device).wait_stream(self.xstream)
+        return self.last
 
 
 def concat_in_pair_order(cnts, xyz_all, bgr_all, pix_all):

@@ -2,9 +2,13 @@
 //   --dump-config <config.yml>   parse only (no GPU): print what CManageData::Init read, as JSON
 //   --decode <in> <out.pnm> [gray]   decode one image file with the native readers (no GPU) and write it as PNM
 //   --dump-yaml <file.yml>       parse only: print every node the OpenCV-YAML reader found, as JSON
+//   --decode-bench <in> <reps>   time the native decoder on one file (colour), print JSON
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
+#include <algorithm>
 #include <chrono>
 #include <string>
 
@@ -87,6 +91,28 @@ int main(int Argc, char** Argv) {
       return 1;
     }
     return sbcv::imwrite_pnm(Argv[3], img) ? 0 : 1;
+  }
+  if (Argc >= 4 && strcmp(Argv[1], "--decode-bench") == 0) {
+    FILE* fp = fopen(Argv[2], "rb");
+    if (!fp) { printf("cannot open %s\n", Argv[2]); return 1; }
+    std::string bytes;
+    char buf[1 << 16];
+    for (size_t n; (n = fread(buf, 1, sizeof buf, fp)) > 0;) bytes.append(buf, n);
+    fclose(fp);
+    const int reps = atoi(Argv[3]) > 0 ? atoi(Argv[3]) : 1;
+    sbcv::Mat img;
+    double best = 1e30;
+    for (int r = 0; r < reps; r++) {
+      const auto t0 = std::chrono::steady_clock::now();
+      if (!sbcv::imdecode(reinterpret_cast<const uint8_t*>(bytes.data()), bytes.size(), img, false)) {
+        printf("decode error: %s\n", sbcv::imread_error().c_str());
+        return 1;
+      }
+      best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+    }
+    printf("{\"width\": %d, \"height\": %d, \"file_bytes\": %zu, \"best_ms\": %.3f, \"Mpix_per_s\": %.2f}\n", img.cols, img.rows, bytes.size(),
+           1e3 * best, img.cols * (double)img.rows / best / 1e6);
+    return 0;
   }
   if (Argc >= 3 && strcmp(Argv[1], "--dump-yaml") == 0) {
     sbcv::FileStorage fs(Argv[2], sbcv::FileStorage::READ);

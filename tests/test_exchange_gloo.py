@@ -80,3 +80,69 @@ def test_pair_sharding_map():
         assert all(exchange.pair_to_rank(p, world) == p % world for p in range(10))
     assert exchange.pairs_of_rank(3, 8, 10) == [3]
     assert exchange.pairs_of_rank(1, 8, 10) == [1, 9]
+
+
+def _ordered_worker(rank, world, port, q):
+    """Two producer threads (contexts) per rank, three pairs each, submitted in whatever order the threads get there."""
+    import threading
+    import time
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cap, NP, STEPS = 48, 2, 3
+        seen = []
+
+        def on_gathered(ticket, cnts, xa, ba, pa):
+            fx, fb, fp = exchange.concat_in_pair_order(cnts, xa, ba, pa)
+            seen.append((ticket, cnts.tolist(), fx.numpy().copy(), fb.numpy().copy(), fp.numpy().copy()))
+
+        ex = exchange.OrderedPointExchange(NP, NP * STEPS, on_gathered=on_gathered)
+
+        def producer(k):
+            xyz = torch.zeros((cap, 3), dtype=torch.float64)
+            bgr = torch.zeros((cap, 3), dtype=torch.uint8)
+            pix = torch.zeros(cap, dtype=torch.int32)
+            for seq in range(STEPS):
+                time.sleep(0.01 * ((rank + k + seq) % 3))  # ranks and contexts drift apart
+                n = 5 + 7 * rank + 3 * k + seq
+                x, b, p = _points(1000 * rank + 10 * k + seq, n)
+                xyz[:n] = torch.from_numpy(x); bgr[:n] = torch.from_numpy(b); pix[:n] = torch.from_numpy(p)
+                ex.submit(k, seq, xyz, bgr, pix, n)
+                xyz.fill_(-1.0); bgr.fill_(9); pix.fill_(-3)  # the next pair's matching overwrites the buffers
+
+        th = [threading.Thread(target=producer, args=(k,)) for k in range(NP)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        ex.finish()
+        q.put((rank, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ordered_exchange_several_pairs_in_flight():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ordered_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank in range(world):
+        seen = got[rank]
+        assert [t for t, *_ in seen] == list(range(6))  # gathers were issued in ticket order on every rank
+        for ticket, cnts, fx, fb, fp in seen:
+            seq, k = divmod(ticket, 2)
+            exp_counts = [5 + 7 * r + 3 * k + seq for r in range(world)]
+            assert cnts == exp_counts
+            ex = np.concatenate([_points(1000 * r + 10 * k + seq, exp_counts[r])[0] for r in range(world)])
+            eb = np.concatenate([_points(1000 * r + 10 * k + seq, exp_counts[r])[1] for r in range(world)])
+            ep = np.concatenate([_points(1000 * r + 10 * k + seq, exp_counts[r])[2] for r in range(world)])
+            assert np.array_equal(fx.view(np.int64), ex.view(np.int64)) and np.array_equal(fb, eb) and np.array_equal(fp, ep), (rank, ticket)
