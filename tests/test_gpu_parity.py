@@ -221,3 +221,44 @@ def test_error_paths(lib):
         g.run_stage(0, st)
     with pytest.raises(capi.StereoError):  # the reference exit(0)s in SetBoundary_smooth
         g.run_stage(0, 6)
+
+
+def test_pairs_in_flight_are_independent(lib):
+    """Several contexts on one GPU, one host thread each (what bench.py and the C++ mirror do): every pair's
+    disparity maps and points equal, bit for bit, those of the same pair processed alone."""
+    import threading
+
+    L, w0, h0 = 3, 96, 72
+    pairs = [synth.make_pair(w0, h0, L, pair_id=20 + k) for k in range(3)]
+    cap = pairs[0].top_size[0] * pairs[0].top_size[1]
+
+    def run(g, sp, out):
+        xyz = np.empty((cap, 3))
+        pix = np.empty(cap, np.int32)
+        for _ in range(3):  # keep the contexts overlapping for a while
+            n = g.match_pair_host(*sp.image, *sp.mask, sp.Q, sp.R_final, sp.T_final, xyz, None, pix, cap)
+        out.append((n, xyz[:n].copy(), pix[:n].copy(), g.get_disparity(0).copy(), g.get_disparity(1).copy()))
+
+    alone = []
+    g = capi.StereoB200(L, w0, h0)
+    for sp in pairs:
+        run(g, sp, alone)
+    g.close()
+    ctxs = [capi.StereoB200(L, w0, h0) for _ in pairs]
+    outs = [[] for _ in pairs]
+    th = [threading.Thread(target=run, args=(ctxs[k], pairs[k], outs[k])) for k in range(3)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    for k in range(3):
+        assert outs[k], f"context {k} failed"
+        n, xyz, pix, d0, d1 = outs[k][0]
+        rn, rxyz, rpix, rd0, rd1 = alone[k]
+        assert n == rn and n > 0
+        _check(xyz, rxyz, f"pair {k}: points")
+        assert np.array_equal(pix, rpix)
+        _check(d0, rd0, f"pair {k}: disparity[0]")
+        _check(d1, rd1, f"pair {k}: disparity[1]")
+    for c in ctxs:
+        c.close()
