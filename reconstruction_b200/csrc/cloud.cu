@@ -42,13 +42,22 @@ __global__ void __launch_bounds__(256) k_cloud_flags(const double* __restrict__ 
   int cnt = 0;
   for (int x = m.XL + threadIdx.x; x <= m.XR; x += blockDim.x) {
     bool ok = disp[(size_t)y * W + x] != (double)SB_NOMATCH;
-    for (int i = 0; i < ks && ok; i++) {
-      const int sy = y + i - a;
-      const int j1 = j12[i], j2 = j12[ks + i];
-      if (sy < 0 || sy >= H || j2 <= j1) continue;  // rows outside the image do not constrain
-      const int xa = max(x + j1 - a, 0), xb = min(x + j2 - 1 - a, W - 1);
-      if (xb < xa) continue;
-      ok = (int)run[(size_t)sy * W + xb] >= xb - xa + 1;
+    // element rows in groups of eight: the eight run-length lookups of a group are independent loads (a row-by-row early
+    // exit chains up to ks dependent memory round trips per pixel); the AND is the same
+    for (int i0 = 0; i0 < ks && ok; i0 += 8) {
+      bool all = true;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int i = i0 + u;
+        if (i >= ks) break;
+        const int sy = y + i - a;
+        const int j1 = j12[i], j2 = j12[ks + i];
+        if (sy < 0 || sy >= H || j2 <= j1) continue;  // rows outside the image do not constrain
+        const int xa = max(x + j1 - a, 0), xb = min(x + j2 - 1 - a, W - 1);
+        if (xb < xa) continue;
+        all &= (int)run[(size_t)sy * W + xb] >= xb - xa + 1;
+      }
+      ok = all;
     }
     flag[(size_t)y * W + x] = ok;
     cnt += ok;

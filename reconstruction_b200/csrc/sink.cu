@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
         }
         const int excl = incl - s;
         if (pass == 0) total = __shfl_sync(0xffffffffu, incl, 31);
-        if (pass == 0 && total < want) { enough = false; break; }
+        if (pass == 0 && total < want) { enough = false; __syncwarp(); break; }
         const bool mine = excl <= rank && rank < incl;
         const unsigned who = __ballot_sync(0xffffffffu, mine);
         const int src = __ffs(who) - 1;
@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
       if (lane == 0 && R > 1) atomicAdd(counters, 1ull);
       break;
     }
+    __syncwarp();  // the next query reuses this warp's histogram and staged keys
     if (lane == 0) mean_dist[__float_as_int(q.w)] = result;
   }
 }
