@@ -52,12 +52,14 @@ bool CStereoMatching::Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Qo, sbcv::
   sbcv::FileStorage fs(staged_name(m_data->m_FilePath, CamPair, ".yml"), sbcv::FileStorage::READ);
   if (!fs.isOpened()) {  // ---- (1) native ----
     sbcv::Mat src[2], msk[2];
+    const bool pf = prefetch_ && prefetch_->active();  // decoded ahead by the host thread pool (MatchAllLayer), else read here
     for (int j = 0; j < 2; j++) {
-      if (!sbcv::imread(cur[j].image_name, src[j], false)) {
+      if (!(pf ? prefetch_->get(cur[j].image_name, false, src[j]) : sbcv::imread(cur[j].image_name, src[j], false))) {
         printf("read image %s error\n", cur[j].image_name.c_str());  // :147-151
         return false;
       }
-      if (!sbcv::imread(cur[j].mask_name, msk[j], true) || msk[j].cols != src[j].cols || msk[j].rows != src[j].rows) {
+      if (!(pf ? prefetch_->get(cur[j].mask_name, true, msk[j]) : sbcv::imread(cur[j].mask_name, msk[j], true)) || msk[j].cols != src[j].cols ||
+          msk[j].rows != src[j].rows) {
         printf("read image %s error\n", cur[j].mask_name.c_str());
         return false;
       }
@@ -223,6 +225,28 @@ void CStereoMatching::MatchAllLayer() {
   const int G = (int)ctxs.size();
   std::vector<PairResult> results(P);
   const auto t0 = std::chrono::steady_clock::now();
+  // native Rectify path (no staged/pairN.yml): decode every distinct frame and mask once, in the order the pairs need them, on
+  // a pool of host threads that runs ahead of the GPU workers
+  sbcv::ImagePrefetcher prefetcher;
+  {
+    std::vector<std::pair<std::string, bool>> req;
+    for (int p = 0; p < P; p++) {
+      FILE* staged = fopen(staged_name(m_data->m_FilePath, p, ".yml").c_str(), "rb");
+      if (staged) { fclose(staged); continue; }
+      for (int j = 0; j < 2; j++) {
+        req.emplace_back(m_data->cam[p][j].image_name, false);
+        req.emplace_back(m_data->cam[p][j].mask_name, true);
+      }
+    }
+    int nt = decode_threads;
+    if (nt <= 0) {
+      const char* e = getenv("SB200_DECODE_THREADS");
+      nt = e ? atoi(e) : (int)std::thread::hardware_concurrency();
+      if (nt > 16) nt = 16;
+    }
+    if (!req.empty() && nt > 0) prefetcher.start(req, nt);
+  }
+  prefetch_ = &prefetcher;
   if (G == 1) {
     for (int p = 0; p < P; p++) {
       printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
@@ -240,6 +264,7 @@ void CStereoMatching::MatchAllLayer() {
       });
     for (auto& w : workers) w.join();
   }
+  prefetch_ = nullptr;
   gpu_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // hand the results to the sink in pair order: InsertPoint per point, then filter(pair) (:29-31,751)
   for (int p = 0; p < P; p++) {

@@ -30,6 +30,7 @@ class CStereoMatching {
   // --- additions of the mirror (not in the reference) ---
   std::vector<int> devices;        // CUDA devices to use; empty = SB200_DEVICES or every visible device
   int contexts_per_device = 0;     // camera pairs in flight per device; <= 0 = SB200_CTX_PER_DEVICE or 3
+  int decode_threads = 0;          // host threads decoding the input files ahead of the GPU; <= 0 = SB200_DECODE_THREADS or the core count (max 16)
   int last_status = 0;             // sb200 status of the last failing call, 0 if none
   std::string last_error;
   double gpu_seconds = 0;          // wall time spent inside the C ABI (all pairs)
@@ -40,4 +41,5 @@ class CStereoMatching {
   bool Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf, bool& staged_on_device);  // :117-168
   bool RunPair(sb200_ctx* ctx, int CamPair, PairResult& out);
   sb200_ctx* last_ctx_ = nullptr;
+  sbcv::ImagePrefetcher* prefetch_ = nullptr;  // original frames and masks, decoded ahead of the GPU (native Rectify path)
 };

@@ -3,6 +3,8 @@
 //   --decode <in> <out.pnm> [gray]   decode one image file with the native readers (no GPU) and write it as PNM
 //   --dump-yaml <file.yml>       parse only: print every node the OpenCV-YAML reader found, as JSON
 //   --decode-bench <in> <reps>   time the native decoder on one file (colour), print JSON
+//   --prefetch-test <threads> <files...>   decode every file (colour and grey, each requested twice) through the
+//                                background ImagePrefetcher; print "<file> <mode> <cols> <rows> <fnv1a>" per consumer
 #include <stdio.h>
 #include <string.h>
 
@@ -11,6 +13,8 @@
 #include <algorithm>
 #include <chrono>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "CReconstruction.h"
 
@@ -91,6 +95,33 @@ int main(int Argc, char** Argv) {
       return 1;
     }
     return sbcv::imwrite_pnm(Argv[3], img) ? 0 : 1;
+  }
+  if (Argc >= 4 && strcmp(Argv[1], "--prefetch-test") == 0) {
+    std::vector<std::pair<std::string, bool>> req;
+    for (int rep = 0; rep < 2; rep++)
+      for (int i = 3; i < Argc; i++) {
+        req.emplace_back(Argv[i], false);
+        req.emplace_back(Argv[i], true);
+      }
+    sbcv::ImagePrefetcher pf;
+    pf.start(req, atoi(Argv[2]));
+    int bad = 0;
+    for (const auto& r : req) {
+      sbcv::Mat m;
+      std::string err;
+      if (!pf.get(r.first, r.second, m, &err)) {
+        printf("%s %s error %s\n", r.first.c_str(), r.second ? "gray" : "color", err.c_str());
+        bad++;
+        continue;
+      }
+      unsigned long long h = 1469598103934665603ull;
+      for (size_t k = 0; k < m.total_bytes(); k++) h = (h ^ m.data[k]) * 1099511628211ull;
+      printf("%s %s %d %d %016llx\n", r.first.c_str(), r.second ? "gray" : "color", m.cols, m.rows, h);
+    }
+    sbcv::Mat extra;
+    std::string err;
+    if (Argc > 3 && pf.get(Argv[3], false, extra, &err) && !extra.empty()) printf("%s color served after its last consumer\n", Argv[3]);
+    return bad ? 1 : 0;
   }
   if (Argc >= 4 && strcmp(Argv[1], "--decode-bench") == 0) {
     FILE* fp = fopen(Argv[2], "rb");

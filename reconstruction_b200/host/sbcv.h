@@ -7,6 +7,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace sbcv {
@@ -98,5 +99,27 @@ bool imwrite_pnm(const std::string& path, const Mat& m);
 bool imread(const std::string& path, Mat& out, bool grayscale);
 bool imdecode(const uint8_t* bytes, size_t n, Mat& out, bool grayscale);
 const std::string& imread_error();  // why the last imread / imdecode of this thread failed
+
+// Background decoding of a list of image files on a pool of host threads (sbimg.cpp).  The matcher needs two frames and two
+// masks per camera pair, adjacent pairs share a camera, and a 12-megapixel JPEG takes a few hundred milliseconds to decode —
+// ten times the GPU time of the pair — so the host mirror decodes every distinct file once, ahead of the GPU, in request order.
+class ImagePrefetcher {
+ public:
+  ImagePrefetcher();
+  ~ImagePrefetcher();
+  // requests: (path, grayscale) in the order they will be needed (duplicates allowed: they share one decode)
+  void start(const std::vector<std::pair<std::string, bool>>& requests, int n_threads);
+  bool active() const;
+  // Blocks until the file has been decoded.  Every get() consumes one of the requests made for (path, grayscale); the cached
+  // image is dropped with the last one.  False (with the decoder's message in *err) when decoding failed or the file was
+  // never requested.
+  bool get(const std::string& path, bool grayscale, Mat& out, std::string* err = nullptr);
+
+ private:
+  struct Impl;
+  Impl* impl_;
+  ImagePrefetcher(const ImagePrefetcher&) = delete;
+  ImagePrefetcher& operator=(const ImagePrefetcher&) = delete;
+};
 
 }  // namespace sbcv

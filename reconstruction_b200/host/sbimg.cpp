@@ -13,12 +13,19 @@
 //         RGB by libpng's 15-bit coefficients for the 0.299 / 0.587 OpenCV passes.
 //   BMP   uncompressed 24 / 32 bit.       PNM   P5 / P6 (sbcv.cpp).
 // EXIF orientation is ignored (as OpenCV 2.4.5 did).
+#pragma GCC optimize("O3")  // the per-row loops below are written to vectorise
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
 
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "sbcv.h"
@@ -110,6 +117,7 @@ struct Comp {
   int pitch = 0;
   std::vector<uint8_t> plane;
   int pred = 0;
+  bool needed = true;  // false: entropy-decoded only (chroma of a colour file read as grey: jpeg_component_info.component_needed)
 };
 
 // jidctint.c (jpeg_idct_islow): CONST_BITS 13, PASS1_BITS 2
@@ -155,6 +163,10 @@ void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int pitch)
   for (int r = 0; r < 8; r++) {
     const int64_t* w = ws + r * 8;
     uint8_t* o = out + (size_t)r * pitch;
+    if ((w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0) {  // jidctint.c's zero-AC row: the same value as the full pass
+      memset(o, range_limit(descale(w[0], 5)), 8);
+      continue;
+    }
     int64_t z2 = w[2], z3 = w[6];
     int64_t z1 = (z2 + z3) * F0_541;
     int64_t tmp2 = z1 + z3 * -(int64_t)F1_847, tmp3 = z1 + z2 * F0_765;
@@ -178,6 +190,7 @@ void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int pitch)
 struct Jpeg {
   const uint8_t* d;
   size_t n;
+  bool want_gray = false;  // only component 0 is reconstructed
   std::string err;
   int W = 0, H = 0, nc = 0, hmax = 1, vmax = 1, restart = 0;
   bool adobe = false;
@@ -189,31 +202,49 @@ struct Jpeg {
 
   static int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
 
-  bool decode_block(BitReader& br, Comp& c, int16_t* coef) {
+  // Returns the zigzag position of the last non-zero coefficient (0 = DC only), or -1 on corrupt data.  A code and the value
+  // bits that follow it (at most 16 + 15 bits) are taken from one look at the 64-bit accumulator.
+  int decode_block(BitReader& br, Comp& c, int16_t* coef) {
     memset(coef, 0, 64 * sizeof(int16_t));
     const Huff& dc = hdc[c.td];
     const Huff& ac = hac[c.ta];
     int s = huff_decode(br, dc);
-    if (s < 0 || s > 15) return false;
+    if (s < 0 || s > 15) return -1;
     const int diff = s ? extend(br.get(s), s) : 0;
     c.pred += diff;
     coef[0] = (int16_t)c.pred;
+    int last = 0;
     for (int k = 1; k < 64;) {
-      const int rs = huff_decode(br, ac);
-      if (rs < 0) return false;
+      if (br.n < 32) br.fill();
+      const int look = (int)(br.acc >> 48);
+      int len, rs;
+      const uint16_t f = ac.fast[look >> 7];
+      if (f) { len = f >> 8; rs = f & 255; }
+      else {
+        len = 0; rs = -1;
+        for (int l = 10; l <= 16; l++) {
+          const int code = look >> (16 - l);
+          if (ac.maxcode[l] >= 0 && code <= ac.maxcode[l] && code >= ac.mincode[l]) { len = l; rs = ac.vals[ac.valptr[l] + code - ac.mincode[l]]; break; }
+        }
+        if (rs < 0) return -1;
+      }
       const int r = rs >> 4;
       s = rs & 15;
       if (s == 0) {
+        br.skip(len);
         if (r != 15) break;
         k += 16;
         continue;
       }
       k += r;
-      if (k > 63) return false;
-      coef[kZigzag[k]] = (int16_t)extend(br.get(s), s);
+      if (k > 63) return -1;
+      const int bits = (int)((br.acc << len) >> (64 - s));
+      br.skip(len + s);
+      coef[kZigzag[k]] = (int16_t)extend(bits, s);
+      last = k;
       k++;
     }
-    return true;
+    return last;
   }
 
   // one scan: `sc` lists component indices.  Interleaved scans walk MCUs; a single-component scan walks that component's own
@@ -244,9 +275,18 @@ struct Jpeg {
           const int nh = inter ? c.h : 1, nv = inter ? c.v : 1;
           for (int by = 0; by < nv; by++)
             for (int bx = 0; bx < nh; bx++) {
-              if (!decode_block(br, c, coef)) { err = "corrupt entropy-coded data"; return false; }
+              const int last = decode_block(br, c, coef);
+              if (last < 0) { err = "corrupt entropy-coded data"; return false; }
               const int X = mx * nh + bx, Y = my * nv + by;
-              if (X < c.bw && Y < c.bh) idct_islow(coef, qt[c.tq], c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8, c.pitch);
+              if (X < c.bw && Y < c.bh && c.needed) {
+                uint8_t* dst = c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8;
+                if (last == 0) {  // DC only: both passes of jidctint.c reduce to one value for the whole block
+                  const uint8_t v = range_limit(descale((int64_t)coef[0] * qt[c.tq][0] * 4, 5));
+                  for (int r = 0; r < 8; r++) memset(dst + (size_t)r * c.pitch, v, 8);
+                } else {
+                  idct_islow(coef, qt[c.tq], dst, c.pitch);
+                }
+              }
             }
         }
         if (restart) until_restart--;
@@ -323,7 +363,8 @@ struct Jpeg {
           c.bw = mcux * c.h; c.bh = mcuy * c.v;
           c.dw = (W * c.h + hmax - 1) / hmax; c.dh = (H * c.v + vmax - 1) / vmax;
           c.pitch = c.bw * 8;
-          c.plane.assign((size_t)c.pitch * c.bh * 8, 0);
+          c.needed = !(want_gray && nc == 3 && i > 0);
+          if (c.needed) c.plane.assign((size_t)c.pitch * c.bh * 8, 0);
         }
         have_sof = true;
       } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
@@ -362,117 +403,103 @@ struct Jpeg {
   }
 
   // jdsample.c: fancy (triangle) upsampling where libjpeg uses it (downsampled_width > 2), replication otherwise.
-  // Rows above the first / below the last real sample row replicate it (jdmainct.c context rows).
-  void upsample(const Comp& c, std::vector<uint8_t>& out) const {
-    const int ow = W, oh = H;
-    out.assign((size_t)ow * oh, 0);
+  // Rows above the first / below the last real sample row replicate it (jdmainct.c context rows).  One output row at a time
+  // (`dst` holds at least 2 * downsampled_width + 2 bytes), so no full-resolution plane is ever materialised.
+  void upsample_row(const Comp& c, int y, uint8_t* __restrict__ dst) const {
     const int hx = hmax / c.h, vx = vmax / c.v;
     const bool exact = hmax % c.h == 0 && vmax % c.v == 0;
     const int n = c.dw;
     auto row = [&](int r) { r = r < 0 ? 0 : (r >= c.dh ? c.dh - 1 : r); return c.plane.data() + (size_t)r * c.pitch; };
-    if (exact && hx == 1 && vx == 1) {
-      for (int y = 0; y < oh; y++) memcpy(out.data() + (size_t)y * ow, row(y), ow);
-      return;
-    }
+    if (exact && hx == 1 && vx == 1) { memcpy(dst, row(y), W); return; }
     const bool fancy = n > 2;
-    std::vector<uint8_t> line((size_t)2 * n + 4);
     if (exact && fancy && hx == 2 && vx == 1) {  // h2v1_fancy_upsample
-      for (int y = 0; y < oh; y++) {
-        const uint8_t* in = row(y);
-        line[0] = in[0];
-        line[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
-        for (int i = 1; i < n - 1; i++) {
-          const int v = in[i] * 3;
-          line[2 * i] = (uint8_t)((v + in[i - 1] + 1) >> 2);
-          line[2 * i + 1] = (uint8_t)((v + in[i + 1] + 2) >> 2);
-        }
-        line[2 * n - 2] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
-        line[2 * n - 1] = in[n - 1];
-        memcpy(out.data() + (size_t)y * ow, line.data(), ow);
+      const uint8_t* __restrict__ in = row(y);
+      dst[0] = in[0];
+      dst[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+      for (int i = 1; i < n - 1; i++) {
+        const int v = in[i] * 3;
+        dst[2 * i] = (uint8_t)((v + in[i - 1] + 1) >> 2);
+        dst[2 * i + 1] = (uint8_t)((v + in[i + 1] + 2) >> 2);
       }
+      dst[2 * n - 2] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
+      dst[2 * n - 1] = in[n - 1];
       return;
     }
     if (exact && fancy && hx == 2 && vx == 2) {  // h2v2_fancy_upsample
-      for (int y = 0; y < oh; y++) {
-        const int r = y >> 1;
-        const uint8_t* in0 = row(r);
-        const uint8_t* in1 = row((y & 1) ? r + 1 : r - 1);
-        int thiscol = in0[0] * 3 + in1[0], nextcol = in0[1] * 3 + in1[1], lastcol;
-        line[0] = (uint8_t)((thiscol * 4 + 8) >> 4);
-        line[1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
-        lastcol = thiscol; thiscol = nextcol;
-        for (int i = 1; i < n - 1; i++) {
-          nextcol = in0[i + 1] * 3 + in1[i + 1];
-          line[2 * i] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
-          line[2 * i + 1] = (uint8_t)((thiscol * 3 + nextcol + 7) >> 4);
-          lastcol = thiscol; thiscol = nextcol;
-        }
-        line[2 * n - 2] = (uint8_t)((thiscol * 3 + lastcol + 8) >> 4);
-        line[2 * n - 1] = (uint8_t)((thiscol * 4 + 7) >> 4);
-        memcpy(out.data() + (size_t)y * ow, line.data(), ow);
+      const int r = y >> 1;
+      const uint8_t* __restrict__ in0 = row(r);
+      const uint8_t* __restrict__ in1 = row((y & 1) ? r + 1 : r - 1);
+      dst[0] = (uint8_t)(((in0[0] * 3 + in1[0]) * 4 + 8) >> 4);
+      dst[1] = (uint8_t)(((in0[0] * 3 + in1[0]) * 3 + (in0[1] * 3 + in1[1]) + 7) >> 4);
+      for (int i = 1; i < n - 1; i++) {  // column sums recomputed per column: independent iterations (vectorisable)
+        const int last = in0[i - 1] * 3 + in1[i - 1], cur = in0[i] * 3 + in1[i], next = in0[i + 1] * 3 + in1[i + 1];
+        dst[2 * i] = (uint8_t)((cur * 3 + last + 8) >> 4);
+        dst[2 * i + 1] = (uint8_t)((cur * 3 + next + 7) >> 4);
       }
+      const int cur = in0[n - 1] * 3 + in1[n - 1], last = in0[n - 2] * 3 + in1[n - 2];
+      dst[2 * n - 2] = (uint8_t)((cur * 3 + last + 8) >> 4);
+      dst[2 * n - 1] = (uint8_t)((cur * 4 + 7) >> 4);
       return;
     }
     if (exact && hx == 1 && vx == 2) {  // h1v2_fancy_upsample (libjpeg-turbo; no width condition)
-      for (int y = 0; y < oh; y++) {
-        const int r = y >> 1;
-        const uint8_t* in0 = row(r);
-        const uint8_t* in1 = row((y & 1) ? r + 1 : r - 1);
-        const int bias = (y & 1) ? 2 : 1;
-        uint8_t* o = out.data() + (size_t)y * ow;
-        for (int x = 0; x < ow; x++) o[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
-      }
+      const int r = y >> 1;
+      const uint8_t* __restrict__ in0 = row(r);
+      const uint8_t* __restrict__ in1 = row((y & 1) ? r + 1 : r - 1);
+      const int bias = (y & 1) ? 2 : 1;
+      for (int x = 0; x < W; x++) dst[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
       return;
     }
     // replication (int_upsample / h2v1_upsample / h2v2_upsample); non-integral ratios are approximated the same way
-    for (int y = 0; y < oh; y++) {
-      const uint8_t* in = row(exact ? y / vx : y * c.v / vmax);
-      uint8_t* o = out.data() + (size_t)y * ow;
-      for (int x = 0; x < ow; x++) {
-        int sx = exact ? x / hx : x * c.h / hmax;
-        if (sx >= n) sx = n - 1;
-        o[x] = in[sx];
-      }
+    const uint8_t* in = row(exact ? y / vx : y * c.v / vmax);
+    for (int x = 0; x < W; x++) {
+      int sx = exact ? x / hx : x * c.h / hmax;
+      if (sx >= n) sx = n - 1;
+      dst[x] = in[sx];
     }
   }
 
   bool to_mat(Mat& out, bool gray) {
-    std::vector<uint8_t> pl[3];
     const bool rgb_coded = nc == 3 && ((adobe && adobe_transform == 0) || (!adobe && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B'));
+    size_t line_len = (size_t)W + 8;
+    for (int i = 0; i < nc; i++) line_len = std::max(line_len, (size_t)2 * comp[i].dw + 8);
+    std::vector<uint8_t> lines(3 * line_len);
+    uint8_t* ln[3] = {lines.data(), lines.data() + line_len, lines.data() + 2 * line_len};
     if (gray) {
       if (rgb_coded) { err = "grey output of an RGB-coded JPEG is not supported"; return false; }
-      upsample(comp[0], pl[0]);  // luma is never subsampled in practice; handled anyway
       out.create(H, W, SB_8UC1);
-      memcpy(out.data, pl[0].data(), (size_t)W * H);
+      for (int y = 0; y < H; y++) {  // luma is never subsampled in practice; handled anyway
+        upsample_row(comp[0], y, ln[0]);
+        memcpy(out.ptr<uint8_t>(y), ln[0], W);
+      }
       return true;
     }
     out.create(H, W, SB_8UC3);
-    if (nc == 1) {
-      upsample(comp[0], pl[0]);
-      for (size_t i = 0; i < (size_t)W * H; i++) out.data[3 * i] = out.data[3 * i + 1] = out.data[3 * i + 2] = pl[0][i];
-      return true;
-    }
-    for (int i = 0; i < 3; i++) upsample(comp[i], pl[i]);
-    if (rgb_coded) {
-      for (size_t i = 0; i < (size_t)W * H; i++) { out.data[3 * i] = pl[2][i]; out.data[3 * i + 1] = pl[1][i]; out.data[3 * i + 2] = pl[0][i]; }
-      return true;
-    }
-    // jdcolor.c build_ycc_rgb_table / ycc_rgb_convert: SCALEBITS 16
-    int cr_r[256], cb_b[256];
-    long cr_g[256], cb_g[256];
-    for (int i = 0; i < 256; i++) {
-      const long x = i - 128;
-      cr_r[i] = (int)((91881L * x + 32768L) >> 16);    // FIX(1.40200)
-      cb_b[i] = (int)((116130L * x + 32768L) >> 16);   // FIX(1.77200)
-      cr_g[i] = -46802L * x;                           // FIX(0.71414)
-      cb_g[i] = -22554L * x + 32768L;                  // FIX(0.34414)
-    }
-    auto clamp = [](int v) { return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v)); };
-    for (size_t i = 0; i < (size_t)W * H; i++) {
-      const int y = pl[0][i], cb = pl[1][i], cr = pl[2][i];
-      out.data[3 * i + 2] = clamp(y + cr_r[cr]);
-      out.data[3 * i + 1] = clamp(y + (int)((cb_g[cb] + cr_g[cr]) >> 16));
-      out.data[3 * i + 0] = clamp(y + cb_b[cb]);
+    for (int y = 0; y < H; y++) {
+      uint8_t* __restrict__ o = out.ptr<uint8_t>(y);
+      for (int i = 0; i < nc; i++) upsample_row(comp[i], y, ln[i]);
+      const uint8_t* __restrict__ p0 = ln[0];
+      if (nc == 1) {
+        for (int x = 0; x < W; x++) o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = p0[x];
+        continue;
+      }
+      const uint8_t* __restrict__ p1 = ln[1];
+      const uint8_t* __restrict__ p2 = ln[2];
+      if (rgb_coded) {
+        for (int x = 0; x < W; x++) { o[3 * x] = p2[x]; o[3 * x + 1] = p1[x]; o[3 * x + 2] = p0[x]; }
+        continue;
+      }
+      // jdcolor.c ycc_rgb_convert, SCALEBITS 16: the table entries written out as arithmetic (FIX(1.40200) = 91881,
+      // FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554, ONE_HALF = 32768; arithmetic right shifts)
+      for (int x = 0; x < W; x++) {
+        const int yy = p0[x], cb = p1[x] - 128, cr = p2[x] - 128;
+        int r = yy + ((91881 * cr + 32768) >> 16);
+        int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+        int b = yy + ((116130 * cb + 32768) >> 16);
+        r = r < 0 ? 0 : (r > 255 ? 255 : r);
+        g = g < 0 ? 0 : (g > 255 ? 255 : g);
+        b = b < 0 ? 0 : (b > 255 ? 255 : b);
+        o[3 * x] = (uint8_t)b; o[3 * x + 1] = (uint8_t)g; o[3 * x + 2] = (uint8_t)r;
+      }
     }
     return true;
   }
@@ -647,6 +674,7 @@ bool imdecode(const uint8_t* d, size_t n, Mat& out, bool grayscale) {
   if (n >= 2 && d[0] == 0xFF && d[1] == 0xD8) {
     Jpeg j;
     j.d = d; j.n = n;
+    j.want_gray = grayscale;
     memset(j.qt, 0, sizeof j.qt);
     if (!j.parse() || !j.to_mat(out, grayscale)) { g_imread_error = j.err; out.release(); return false; }
     return true;
@@ -682,6 +710,85 @@ bool imread(const std::string& path, Mat& out, bool grayscale) {
   fclose(fp);
   if (!ok) { g_imread_error = "read error"; return false; }
   return imdecode(buf.data(), buf.size(), out, grayscale);
+}
+
+// ---------------------------------------------------------------------------------------------- ImagePrefetcher
+struct ImagePrefetcher::Impl {
+  struct Entry {
+    std::string path;
+    bool gray = false;
+    int users = 0;
+    bool done = false, ok = false;
+    std::string err;
+    Mat img;
+  };
+  std::vector<Entry> entries;                       // distinct (path, gray), in first-request order
+  std::map<std::pair<std::string, bool>, size_t> index;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::atomic<size_t> next{0};
+  std::vector<std::thread> threads;
+  void work() {
+    for (;;) {
+      const size_t i = next.fetch_add(1);
+      if (i >= entries.size()) return;
+      Mat m;
+      const bool ok = imread(entries[i].path, m, entries[i].gray);
+      const std::string e = ok ? std::string() : imread_error();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        entries[i].img = m;
+        entries[i].ok = ok;
+        entries[i].err = e;
+        entries[i].done = true;
+      }
+      cv.notify_all();
+    }
+  }
+};
+
+ImagePrefetcher::ImagePrefetcher() : impl_(new Impl) {}
+ImagePrefetcher::~ImagePrefetcher() {
+  for (std::thread& t : impl_->threads) t.join();
+  delete impl_;
+}
+bool ImagePrefetcher::active() const { return !impl_->entries.empty(); }
+
+void ImagePrefetcher::start(const std::vector<std::pair<std::string, bool>>& requests, int n_threads) {
+  if (active()) return;
+  for (const auto& r : requests) {
+    auto it = impl_->index.find(r);
+    if (it == impl_->index.end()) {
+      impl_->index[r] = impl_->entries.size();
+      Impl::Entry e;
+      e.path = r.first;
+      e.gray = r.second;
+      e.users = 1;
+      impl_->entries.push_back(e);
+    } else {
+      impl_->entries[it->second].users++;
+    }
+  }
+  if (n_threads < 1) n_threads = 1;
+  if ((size_t)n_threads > impl_->entries.size()) n_threads = (int)impl_->entries.size();
+  for (int t = 0; t < n_threads; t++) impl_->threads.emplace_back([this]() { impl_->work(); });
+}
+
+bool ImagePrefetcher::get(const std::string& path, bool grayscale, Mat& out, std::string* err) {
+  out.release();
+  auto it = impl_->index.find(std::make_pair(path, grayscale));
+  if (it == impl_->index.end()) {
+    if (err) *err = "not requested: " + path;
+    return false;
+  }
+  std::unique_lock<std::mutex> lk(impl_->mu);
+  Impl::Entry& e = impl_->entries[it->second];
+  impl_->cv.wait(lk, [&]() { return e.done; });
+  if (err) *err = e.err;
+  const bool ok = e.ok;
+  if (ok) out = e.img;
+  if (--e.users <= 0) e.img.release();  // last consumer: the cache lets go of the pixels
+  return ok;
 }
 
 }  // namespace sbcv

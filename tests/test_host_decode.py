@@ -224,3 +224,30 @@ def test_yaml_edge_cases(cli, tmp_path):
     open(bad, "w").write("%YAML:1.0\nM: !!opencv-matrix\n   rows: 2\n   cols: 2\n   dt: d\n   data: [ 1., 2., 3. ]\n")
     r = subprocess.run([cli, "--dump-yaml", bad], capture_output=True, text=True)
     assert r.returncode != 0 and "rows*cols does not match data" in r.stdout
+
+
+def test_prefetcher_serves_every_consumer(cli, tmp_path):
+    """ImagePrefetcher (the host thread pool that decodes frames ahead of the GPU workers): every request is served with the
+    bytes a direct imread gives, duplicates share one decode, a failing file reports its error and the others still arrive."""
+    names = ["a_420_q90.jpg", "g_grey_q80.jpg", "i_rgb.png", "l.bmp", "b_422_q50_rst.jpg"]
+    files = [os.path.join(GOLD, n) for n in names]
+
+    def fnv(a):
+        h = 1469598103934665603
+        for b in np.ascontiguousarray(a).tobytes():
+            h = ((h ^ b) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+        return f"{h:016x}"
+
+    exp = np.load(os.path.join(GOLD, "decode_expected.npz"))
+    for threads in (1, 4):
+        r = subprocess.run([cli, "--prefetch-test", str(threads)] + files, capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout
+        lines = [ln.split() for ln in r.stdout.strip().splitlines()]
+        assert len(lines) == 4 * len(files) and "served after" not in r.stdout  # the cache drops an image with its last consumer
+        for path, mode, cols, rows, h in lines:
+            ref = exp[f"{os.path.basename(path)}:{mode}"]
+            assert (int(cols), int(rows)) == (ref.shape[1], ref.shape[0]) and h == fnv(ref), (path, mode)
+    bad = str(tmp_path / "broken.jpg")
+    open(bad, "wb").write(open(files[0], "rb").read()[:150])
+    r = subprocess.run([cli, "--prefetch-test", "3", files[0], bad, files[2]], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.count(" error ") == 4 and r.stdout.count(os.path.basename(files[2])) == 4
