@@ -13,7 +13,7 @@
 //         RGB by libpng's 15-bit coefficients for the 0.299 / 0.587 OpenCV passes.
 //   BMP   uncompressed 24 / 32 bit.       PNM   P5 / P6 (sbcv.cpp).
 // EXIF orientation is ignored (as OpenCV 2.4.5 did).
-#pragma GCC optimize("O3")  // the per-row loops below are written to vectorise
+
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
