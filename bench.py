@@ -202,7 +202,6 @@ class _DevArr:
 
 
 def run_ours(args):
-    import numpy as np  # noqa: F401
     import torch
     import torch.distributed as dist
 
@@ -245,7 +244,6 @@ def run_ours(args):
     # order (reconstruction_b200/exchange.py::OrderedPointExchange), so no context ever waits for another rank
     exchange_on = [world > 1]
     xch = [None]
-    aborted = []
 
     def exchange(k, seq, n_local):
         """All-gather of the per-pair point buffers over NCCL, overlapped with the following pairs' matching; the last ones are
@@ -299,7 +297,6 @@ def run_ours(args):
                         npts[k] = step_fn(k, i)
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
-                aborted.append(k)
                 if xch[0] is not None:
                     xch[0].abort(e)
 

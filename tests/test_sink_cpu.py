@@ -62,3 +62,16 @@ def test_sink_filter_record_layout():
     rec, kept, info = so.sink_filter(p64, 20, 1.0, 2.5, [0, 0, 0])
     assert rec.dtype == np.float32 and rec.shape == (len(kept), 7) and np.array_equal(rec[:, :3], p64[kept].astype(np.float32))
     assert np.all(np.diff(kept) > 0) and 0 not in kept
+
+
+def test_oracle_reproduces_the_committed_golden():
+    """tests/golden/sink_small.npz (make_sink_golden.py): the checker has not drifted."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sink_small.npz"))
+    rec, kept, info = so.sink_filter(g["xyz"], int(g["mean_k"]), float(g["std_mul"]), float(g["radius"]), g["cam"])
+    assert np.array_equal(kept, g["kept"]) and np.array_equal(info["mean_dist"], g["mean_dist"])
+    assert [info["mean"], info["stddev"], info["threshold"]] == g["stats"].tolist()
+    assert np.array_equal(rec[:, :3].view(np.int32), g["records"][:, :3].view(np.int32))
+    ok = ~np.isnan(g["records"][:, 3]) & (g["eigen_gap"] > 1e-3)
+    assert np.abs(rec[ok, 3:] - g["records"][ok, 3:]).max() < 1e-6  # eigh across numpy / LAPACK builds

@@ -97,3 +97,14 @@ def test_points_of_a_matched_pair_and_cli(tmp_path):
     assert np.array_equal(np.isnan(got[:, 3]), np.isnan(rec[:, 3]))
     assert (np.abs(np.abs(np.einsum("ij,ij->i", got[both, 3:6], rec[both, 3:6])) - 1) < 1e-5).all()
     assert os.path.exists(str(tmp_path / "out.ply.normals.ply"))
+
+
+def test_committed_golden():
+    """The same call against tests/golden/sink_small.npz (written by the checker, make_sink_golden.py)."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sink_small.npz"))
+    rec, kept, st = capi.sink_filter(g["xyz"], int(g["mean_k"]), float(g["std_mul"]), float(g["radius"]), g["cam"])
+    assert np.array_equal(kept, g["kept"]) and [st["mean"], st["stddev"], st["threshold"]] == g["stats"].tolist()
+    assert np.array_equal(rec[:, :3].view(np.int32), g["records"][:, :3].view(np.int32))
+    ok = ~np.isnan(g["records"][:, 3]) & (g["eigen_gap"] > 1e-3)
+    assert np.array_equal(np.isnan(rec[:, 3]), np.isnan(g["records"][:, 3]))
+    assert np.abs(rec[ok, 3:6] - g["records"][ok, 3:6]).max() < 2e-5 and np.allclose(rec[ok, 6], g["records"][ok, 6], rtol=1e-4, atol=1e-7)
