@@ -94,7 +94,7 @@ class FileStorage {
 bool imread_pnm(const std::string& path, Mat& out, bool grayscale);
 bool imwrite_pnm(const std::string& path, const Mat& m);
 
-// cv::imread stand-in (sbimg.cpp): JPEG (baseline), PNG, BMP and PNM by content; BGR or grey 8-bit output, the same bits
+// cv::imread stand-in (sbimg.cpp): JPEG (sequential and progressive Huffman), PNG, BMP and PNM by content; BGR or grey 8-bit output, the same bits
 // OpenCV produces for the file.  `grayscale` = the CV_LOAD_IMAGE_GRAYSCALE flag the reference reads its masks with.
 bool imread(const std::string& path, Mat& out, bool grayscale);
 bool imdecode(const uint8_t* bytes, size_t n, Mat& out, bool grayscale);

@@ -5,10 +5,10 @@
 // ("%.4d_Cam%d.jpg", BatchProcess/main.cpp:66).  OpenCV's codecs are third-party code that is not under /root/reference
 // (OpenCV 2.4.5 wraps libjpeg / libpng), so this restates the published algorithms and is pinned against the OpenCV
 // 4.13 build of this image (libjpeg-turbo, libpng): tests/test_host_decode.py compares bit for bit.
-//   JPEG  baseline / extended sequential Huffman, 8 bit, 1 or 3 components, any scan layout, restart intervals.
+//   JPEG  baseline / extended sequential and progressive Huffman, 8 bit, 1 or 3 components, any scan layout, restart intervals.
 //         Inverse DCT = the "islow" integer LL&M transform, chroma by "fancy" (triangle) upsampling, YCbCr -> RGB by the
 //         16-bit fixed-point tables: libjpeg's default decompression path.  Grey output of a colour file = the Y plane
-//         (what cv::imread(..., 0) asks libjpeg for).  Progressive and arithmetic-coded files are refused.
+//         (what cv::imread(..., 0) asks libjpeg for).  Arithmetic-coded, lossless and hierarchical files are refused.
 //   PNG   all colour types, bit depths 1-16, Adam7 interlace; 16 -> 8 bit by dropping the low byte, alpha dropped, grey from
 //         RGB by libpng's 15-bit coefficients for the 0.299 / 0.587 OpenCV passes.
 //   BMP   uncompressed 24 / 32 bit.       PNM   P5 / P6 (sbcv.cpp).
@@ -117,6 +117,7 @@ struct Comp {
   int pitch = 0;
   std::vector<uint8_t> plane;
   int pred = 0;
+  std::vector<int16_t> coefs;  // progressive files: every block's 64 coefficients (natural order), filled scan by scan
   bool needed = true;  // false: entropy-decoded only (chroma of a colour file read as grey: jpeg_component_info.component_needed)
 };
 
@@ -191,6 +192,7 @@ struct Jpeg {
   const uint8_t* d;
   size_t n;
   bool want_gray = false;  // only component 0 is reconstructed
+  bool progressive = false;
   std::string err;
   int W = 0, H = 0, nc = 0, hmax = 1, vmax = 1, restart = 0;
   bool adobe = false;
@@ -299,6 +301,118 @@ struct Jpeg {
     return true;
   }
 
+  // One scan of a progressive file (ITU T.81 G.1.2; the procedure of libjpeg's jdphuff.c): DC scans may interleave components,
+  // AC scans carry one component and walk its own blocks; first passes (Ah == 0) write coefficient << Al, refinement passes add one
+  // bit of precision to what is already there.
+  bool scan_progressive(const uint8_t*& p, const std::vector<int>& sc, int Ss, int Se, int Ah, int Al) {
+    BitReader br;
+    br.p = p; br.end = d + n;
+    for (int ci : sc) comp[ci].pred = 0;
+    const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
+    const bool inter = sc.size() > 1;
+    Comp& c0 = comp[sc[0]];
+    const int ux = inter ? mcux : (c0.dw + 7) / 8, uy = inter ? mcuy : (c0.dh + 7) / 8;
+    int until_restart = restart;
+    unsigned eobrun = 0;
+    const int p1 = 1 << Al, m1 = -(1 << Al);
+    for (int my = 0; my < uy; my++)
+      for (int mx = 0; mx < ux; mx++) {
+        if (restart && until_restart == 0) {
+          br.reset();
+          const uint8_t* q = br.p;
+          while (q + 1 < d + n && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+          if (q + 1 >= d + n) { err = "missing restart marker"; return false; }
+          br.p = q + 2;
+          for (int ci : sc) comp[ci].pred = 0;
+          eobrun = 0;
+          until_restart = restart;
+        }
+        for (int ci : sc) {
+          Comp& c = comp[ci];
+          const int nh = inter ? c.h : 1, nv = inter ? c.v : 1;
+          for (int by = 0; by < nv; by++)
+            for (int bx = 0; bx < nh; bx++) {
+              const int X = mx * nh + bx, Y = my * nv + by;
+              int16_t scratch[64];
+              int16_t* blk = (X < c.bw && Y < c.bh) ? c.coefs.data() + ((size_t)Y * c.bw + X) * 64 : scratch;
+              if (blk == scratch) memset(scratch, 0, sizeof scratch);
+              if (Ss == 0) {
+                if (Ah == 0) {  // DC first
+                  const int t = huff_decode(br, hdc[c.td]);
+                  if (t < 0 || t > 15) { err = "corrupt entropy-coded data"; return false; }
+                  c.pred += t ? extend(br.get(t), t) : 0;
+                  blk[0] = (int16_t)(c.pred * (1 << Al));
+                } else if (br.get(1)) {  // DC refinement
+                  blk[0] = (int16_t)(blk[0] | p1);
+                }
+                continue;
+              }
+              const Huff& ac = hac[c.ta];
+              if (Ah == 0) {  // AC first
+                if (eobrun > 0) { eobrun--; continue; }
+                for (int k = Ss; k <= Se; k++) {
+                  const int rs = huff_decode(br, ac);
+                  if (rs < 0) { err = "corrupt entropy-coded data"; return false; }
+                  const int r = rs >> 4, t = rs & 15;
+                  if (t) {
+                    k += r;
+                    if (k > 63) { err = "corrupt entropy-coded data"; return false; }
+                    blk[kZigzag[k]] = (int16_t)(extend(br.get(t), t) * (1 << Al));
+                  } else if (r == 15) {
+                    k += 15;
+                  } else {
+                    eobrun = 1u << r;
+                    if (r) eobrun += (unsigned)br.get(r);
+                    eobrun--;
+                    break;
+                  }
+                }
+                continue;
+              }
+              // AC refinement
+              int k = Ss;
+              if (eobrun == 0) {
+                for (; k <= Se; k++) {
+                  const int rs = huff_decode(br, ac);
+                  if (rs < 0) { err = "corrupt entropy-coded data"; return false; }
+                  int r = rs >> 4, t = rs & 15;
+                  if (t) {
+                    t = br.get(1) ? p1 : m1;  // a newly non-zero coefficient (size is always 1)
+                  } else if (r != 15) {
+                    eobrun = 1u << r;
+                    if (r) eobrun += (unsigned)br.get(r);
+                    break;  // end of band: the rest of the block is only refined
+                  }
+                  // skip r still-zero coefficients, refining the non-zero ones on the way
+                  do {
+                    int16_t& v = blk[kZigzag[k]];
+                    if (v != 0) {
+                      if (br.get(1) && (v & p1) == 0) v = (int16_t)(v + (v >= 0 ? p1 : m1));
+                    } else if (--r < 0) {
+                      break;
+                    }
+                    k++;
+                  } while (k <= Se);
+                  if (t && k <= 63) blk[kZigzag[k]] = (int16_t)t;
+                }
+              }
+              if (eobrun > 0) {
+                for (; k <= Se; k++) {
+                  int16_t& v = blk[kZigzag[k]];
+                  if (v != 0 && br.get(1) && (v & p1) == 0) v = (int16_t)(v + (v >= 0 ? p1 : m1));
+                }
+                eobrun--;
+              }
+            }
+        }
+        if (restart) until_restart--;
+      }
+    const uint8_t* q = br.p;
+    while (q + 1 < d + n && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
+    p = q;
+    return true;
+  }
+
   bool parse() {
     if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) { err = "not a JPEG file"; return false; }
     const uint8_t* p = d + 2;
@@ -344,7 +458,8 @@ struct Jpeg {
           h.present = true;
           h.build();
         }
-      } else if (m == 0xC0 || m == 0xC1) {  // SOF0 / SOF1
+      } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1 / SOF2 (progressive)
+        progressive = m == 0xC2;
         if (len < 8 || s[0] != 8) { err = "only 8-bit JPEG is supported"; return false; }
         H = be16(s + 1); W = be16(s + 3); nc = s[5];
         if (W <= 0 || H <= 0 || (nc != 1 && nc != 3) || len < 8 + 3 * nc) { err = "unsupported JPEG frame (components)"; return false; }
@@ -365,10 +480,11 @@ struct Jpeg {
           c.pitch = c.bw * 8;
           c.needed = !(want_gray && nc == 3 && i > 0);
           if (c.needed) c.plane.assign((size_t)c.pitch * c.bh * 8, 0);
+          if (progressive) c.coefs.assign((size_t)c.bw * c.bh * 64, 0);
         }
         have_sof = true;
-      } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
-        err = m == 0xC2 ? "progressive JPEG is not supported" : "unsupported JPEG coding process";
+      } else if (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC) {
+        err = "unsupported JPEG coding process (lossless / hierarchical / arithmetic)";
         return false;
       } else if (m == 0xDD) {
         if (len >= 4) restart = be16(s);
@@ -385,20 +501,35 @@ struct Jpeg {
           if (ci < 0) { err = "bad SOS component"; return false; }
           comp[ci].td = s[2 + 2 * i] >> 4;
           comp[ci].ta = s[2 + 2 * i] & 15;
-          if (comp[ci].td > 3 || comp[ci].ta > 3 || !hdc[comp[ci].td].present || !hac[comp[ci].ta].present || !qt_set[comp[ci].tq]) {
+          const int Ss_ = s[1 + 2 * ns], Ah_ = s[3 + 2 * ns] >> 4;
+          const bool need_dc = !progressive || (Ss_ == 0 && Ah_ == 0), need_ac = !progressive || Ss_ > 0;
+          if (comp[ci].td > 3 || comp[ci].ta > 3 || (need_dc && !hdc[comp[ci].td].present) || (need_ac && !hac[comp[ci].ta].present) ||
+              !qt_set[comp[ci].tq]) {
             err = "scan refers to a missing table";
             return false;
           }
           sc.push_back(ci);
         }
+        const int Ss = s[1 + 2 * ns], Se = s[2 + 2 * ns], Ah = s[3 + 2 * ns] >> 4, Al = s[3 + 2 * ns] & 15;
         p += len;
-        if (!scan(p, sc)) return false;
+        if (progressive) {
+          if (Ss > Se || Se > 63 || (Ss == 0 && Se != 0) || (Ss > 0 && ns != 1) || Al > 13) { err = "bad progressive scan parameters"; return false; }
+          if (!scan_progressive(p, sc, Ss, Se, Ah, Al)) return false;
+        } else if (!scan(p, sc)) return false;
         scans++;
         continue;
       }
       p += len;
     }
     if (!have_sof || scans == 0) { err = "no image data"; return false; }
+    if (progressive)  // all scans are in: reconstruct every block of the components that are wanted
+      for (int i = 0; i < nc; i++) {
+        Comp& c = comp[i];
+        if (!c.needed) continue;
+        for (int Y = 0; Y < c.bh; Y++)
+          for (int X = 0; X < c.bw; X++)
+            idct_islow(c.coefs.data() + ((size_t)Y * c.bw + X) * 64, qt[c.tq], c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8, c.pitch);
+      }
     return true;
   }
 

@@ -31,6 +31,8 @@ def main():
     files["g_grey_q80.jpg"] = b.tobytes()
     ok, b = cv2.imencode(".jpg", texture(24, 24, rng), [cv2.IMWRITE_JPEG_OPTIMIZE, 1, cv2.IMWRITE_JPEG_QUALITY, 97])
     files["h_optimised_q97.jpg"] = b.tobytes()
+    ok, b = cv2.imencode(".jpg", texture(29, 35, rng), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 88, cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+    files["m_progressive_q88_rst.jpg"] = b.tobytes()
     ok, b = cv2.imencode(".png", texture(19, 23, rng))
     files["i_rgb.png"] = b.tobytes()
     ok, b = cv2.imencode(".png", rng.integers(0, 65536, (11, 13, 3)).astype(np.uint16))

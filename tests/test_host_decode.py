@@ -42,7 +42,7 @@ def test_golden_files(cli, tmp_path):
     """Committed files + what OpenCV 4.13 decoded them to: no cv2 needed at test time."""
     exp = np.load(os.path.join(GOLD, "decode_expected.npz"))
     names = sorted({k.split(":")[0] for k in exp.files})
-    assert len(names) == 12
+    assert len(names) == 13
     for name in names:
         for mode in ("color", "gray"):
             got, msg = decode(cli, os.path.join(GOLD, name), str(tmp_path / "o.pnm"), mode == "gray")
@@ -89,13 +89,32 @@ def test_jpeg_matches_opencv(cli, tmp_path):
     assert n == 42
 
 
-def test_progressive_jpeg_is_refused(cli, tmp_path):
+def test_progressive_jpeg_matches_opencv(cli, tmp_path):
+    """SOF2 files (spectral selection + successive approximation: libjpeg's standard script exercises DC / AC first and
+    refinement scans), with restart intervals and every chroma layout."""
     cv2 = pytest.importorskip("cv2")
-    ok, b = cv2.imencode(".jpg", _texture(32, 32, np.random.default_rng(1)), [cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
-    p = str(tmp_path / "p.jpg")
-    open(p, "wb").write(b.tobytes())
+    rng = np.random.default_rng(11)
+    S = [cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_422,
+         cv2.IMWRITE_JPEG_SAMPLING_FACTOR_440, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_411]
+    for (h, w) in [(48, 64), (37, 53), (1, 1), (3, 2), (100, 33)]:
+        for q, sf, rst in [(30, S[0], 0), (75, S[1], 3), (95, S[2], 0), (100, S[3], 2), (85, S[4], 0)]:
+            ok, b = cv2.imencode(".jpg", _texture(h, w, rng), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf,
+                                                                cv2.IMWRITE_JPEG_RST_INTERVAL, rst, cv2.IMWRITE_JPEG_PROGRESSIVE, 1])
+            assert ok and b"\xff\xc2" in b.tobytes()
+            _check_against_cv2(cli, tmp_path, b.tobytes(), ("progressive", h, w, q, hex(sf), rst))
+    ok, b = cv2.imencode(".jpg", _texture(40, 50, rng)[..., 2], [cv2.IMWRITE_JPEG_PROGRESSIVE, 1, cv2.IMWRITE_JPEG_QUALITY, 90])
+    _check_against_cv2(cli, tmp_path, b.tobytes(), "progressive grey")
+
+
+def test_unsupported_jpeg_process_is_refused(cli, tmp_path):
+    """Arithmetic-coded / lossless frames (SOF9, SOF3, ...) are reported, never decoded wrongly."""
+    data = bytearray(open(os.path.join(GOLD, "a_420_q90.jpg"), "rb").read())
+    i = data.index(b"\xff\xc0")
+    data[i + 1] = 0xC9  # SOF9: extended sequential, arithmetic coding
+    p = str(tmp_path / "arith.jpg")
+    open(p, "wb").write(bytes(data))
     got, msg = decode(cli, p, str(tmp_path / "o.pnm"), False)
-    assert got is None and "progressive JPEG is not supported" in msg  # loud, never a silently wrong image
+    assert got is None and "unsupported JPEG coding process" in msg
 
 
 def _chunk(t, d):
