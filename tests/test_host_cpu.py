@@ -66,3 +66,45 @@ def test_missing_config_and_no_gpu(cli, tmp_path):
     cfg, _ = stage.write_dataset(str(tmp_path), 2, 32, 24)
     r = subprocess.run([cli, cfg], capture_output=True, text=True)
     assert r.returncode == 1 and "no CPU path" in r.stdout
+
+
+def test_config_written_like_the_references_batch_tool(cli, tmp_path):
+    """A data-set description produced the way BatchProcess/main.cpp:47-73 produces it — by cv::FileStorage, JPEG frames and JPEG
+    masks, camID as an unsigned-char matrix, the reference's pair list {0,1},{2,3},{4,5},{7,6} (:30-36) — parses into the same
+    CManageData fields; the original size comes from decoding masklist[0] (CManageData.cpp:68-69) with the native JPEG reader."""
+    cv2 = pytest.importorskip("cv2")
+    root = str(tmp_path) + os.sep
+    os.makedirs(root + "mask")
+    n_cam, ow, oh = 8, 72, 56
+    rng = np.random.default_rng(3)
+    for j in range(n_cam):
+        assert cv2.imwrite(root + f"0001_Cam{j}.jpg", rng.integers(0, 256, (oh, ow, 3), dtype=np.uint8))
+        assert cv2.imwrite(root + f"mask/0001_Cam{j}.jpg", np.full((oh, ow), 255, np.uint8))
+    cams = stage.rig_cameras(n_cam, ow, oh)
+    fs = cv2.FileStorage(root + "calib_camera.yml", cv2.FILE_STORAGE_WRITE)
+    for j, (K, Rt) in enumerate(cams):
+        fs.write(f"intrinsic-{j}", K)
+        fs.write(f"extrinsic-{j}", Rt)
+    fs.release()
+    fs = cv2.FileStorage(root + "config.yml", cv2.FILE_STORAGE_WRITE)
+    fs.write("filepath", root)
+    fs.write("outfilename", root + "1.ply")
+    fs.write("isoutput", 0)
+    fs.write("camera_calib_name", "calib_camera.yml")
+    fs.write("PyrmNum", 4)
+    fs.write("LowestLevelWidth", 160)
+    fs.write("LowestLevelHeight", 240)
+    fs.write("imagelist", [f"0001_Cam{j}.jpg" for j in range(n_cam)])
+    fs.write("masklist", [f"mask/0001_Cam{j}.jpg" for j in range(n_cam)])
+    fs.write("camID", np.array([[0, 1], [2, 3], [4, 5], [7, 6]], np.uint8))
+    fs.release()
+    d = json.loads(subprocess.run([cli, "--dump-config", root + "config.yml"], check=True, capture_output=True, text=True).stdout)
+    assert (d["PyrmNum"], d["LowestLevelWidth"], d["LowestLevelHeight"], d["isoutput"]) == (4, 160, 240, 0)
+    assert (d["OriginWidth"], d["OriginHeight"]) == (ow, oh) and d["CameraNum"] == n_cam and d["outfilename"] == root + "1.ply"
+    assert [[p["cam0"]["id"], p["cam1"]["id"]] for p in d["pairs"]] == [[0, 1], [2, 3], [4, 5], [7, 6]]
+    for p in d["pairs"]:
+        for k in ("cam0", "cam1"):
+            c = p[k]
+            K, Rt = cams[c["id"]]
+            assert c["image"] == root + f"0001_Cam{c['id']}.jpg" and c["mask"] == root + f"mask/0001_Cam{c['id']}.jpg"
+            assert np.array_equal(np.array(c["K"]).reshape(3, 3), K) and np.array_equal(np.array(c["Rt"]).reshape(3, 4), Rt)
