@@ -44,7 +44,7 @@ struct Huff {
   uint8_t vals[256] = {0};
   // canonical decoding tables (ITU T.81 F.2.2.3)
   int mincode[17], maxcode[18], valptr[17];
-  uint16_t fast[512];  // 9-bit look-ahead: (length << 8) | symbol, 0 = longer code
+  uint16_t fast[1 << 11];  // 11-bit look-ahead: (length << 8) | symbol, 0 = longer code
   void build() {
     int code = 0, k = 0;
     for (int l = 1; l <= 16; l++) {
@@ -58,10 +58,10 @@ struct Huff {
     maxcode[17] = 0x7fffffff;
     memset(fast, 0, sizeof fast);
     code = 0; k = 0;
-    for (int l = 1; l <= 9; l++) {
+    for (int l = 1; l <= 11; l++) {
       for (int i = 0; i < bits[l]; i++, k++, code++) {
-        const int lo = code << (9 - l);
-        for (int j = 0; j < (1 << (9 - l)); j++) fast[lo + j] = (uint16_t)((l << 8) | vals[k]);
+        const int lo = code << (11 - l);
+        for (int j = 0; j < (1 << (11 - l)); j++) fast[lo + j] = (uint16_t)((l << 8) | vals[k]);
       }
       code <<= 1;
     }
@@ -75,6 +75,20 @@ struct BitReader {
   int n = 0;
   bool hit_marker = false;
   void fill() {
+    // fast path: eight bytes at once when none of them is 0xFF (no stuffing, no marker) — the common case
+    if (!hit_marker && end - p >= 8 && n <= 56) {
+      uint64_t w;
+      memcpy(&w, p, 8);
+      w = __builtin_bswap64(w);
+      const uint64_t x = ~w;  // a 0xFF byte of w is a zero byte of x
+      if (((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull) == 0) {
+        const int k = (64 - n) >> 3;  // whole bytes that fit (>= 1)
+        acc |= (w >> (64 - 8 * k)) << (64 - n - 8 * k);
+        n += 8 * k;
+        p += k;
+        return;
+      }
+    }
     while (n <= 56) {
       int b = 0;
       if (!hit_marker && p < end) {
@@ -96,9 +110,9 @@ struct BitReader {
 
 inline int huff_decode(BitReader& br, const Huff& h) {
   const int look = br.peek(16);
-  const uint16_t f = h.fast[look >> 7];
+  const uint16_t f = h.fast[look >> 5];
   if (f) { br.skip(f >> 8); return f & 255; }
-  for (int l = 10; l <= 16; l++) {
+  for (int l = 12; l <= 16; l++) {
     const int code = look >> (16 - l);
     if (h.maxcode[l] >= 0 && code <= h.maxcode[l] && code >= h.mincode[l]) {
       br.skip(l);
@@ -108,7 +122,8 @@ inline int huff_decode(BitReader& br, const Huff& h) {
   br.skip(16);
   return -1;
 }
-inline int extend(int v, int s) { return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+// T.81 F.2.2.1 EXTEND, branch-free: values whose top bit is clear are negative (v - 2^s + 1)
+inline int extend(int v, int s) { return v + ((((v >> (s - 1)) & 1) - 1) & (1 - (1 << s))); }
 
 struct Comp {
   int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0;
@@ -220,11 +235,11 @@ struct Jpeg {
       if (br.n < 32) br.fill();
       const int look = (int)(br.acc >> 48);
       int len, rs;
-      const uint16_t f = ac.fast[look >> 7];
+      const uint16_t f = ac.fast[look >> 5];
       if (f) { len = f >> 8; rs = f & 255; }
       else {
         len = 0; rs = -1;
-        for (int l = 10; l <= 16; l++) {
+        for (int l = 12; l <= 16; l++) {
           const int code = look >> (16 - l);
           if (ac.maxcode[l] >= 0 && code <= ac.maxcode[l] && code >= ac.mincode[l]) { len = l; rs = ac.vals[ac.valptr[l] + code - ac.mincode[l]]; break; }
         }
