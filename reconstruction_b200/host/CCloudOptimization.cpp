@@ -39,6 +39,35 @@ void CCloudOptimization::InsertPoints(const double* p, const unsigned char* c, s
   else bgr.insert(bgr.end(), 3 * n, (unsigned char)0);
 }
 
+bool CCloudOptimization::FilterPoints(int idx, int device, const double* p, size_t n, std::vector<float>& rec, size_t& kept, double stats[5],
+                                      std::string& err) const {
+  kept = 0;
+  if (n == 0) return true;
+  // CamCenter[idx] = centre of the pair's first camera (:50-51)
+  double cam[3] = {0, 0, 0};
+  if (m_ImageData && idx >= 0 && idx < (int)m_ImageData->cam.size() && !m_ImageData->cam[idx][0].CamCenter.empty())
+    for (int k = 0; k < 3; k++) cam[k] = m_ImageData->cam[idx][0].CamCenter.at<double>(k, 0);
+  rec.resize(7 * n);
+  int64_t k64 = 0;
+  const int rc = sb200_sink_filter(device, p, (int64_t)n, m_sor_meank, m_sor_stdThres, m_mls_radius, cam, rec.data(), nullptr, (int64_t)n, &k64, stats);
+  if (rc != SB200_OK) {
+    err = std::string(sb200_status_string(rc)) + ": " + sb200_sink_last_error();
+    rec.clear();
+    return false;
+  }
+  kept = (size_t)k64;
+  rec.resize(7 * kept);
+  return true;
+}
+
+void CCloudOptimization::StoreFiltered(int idx, std::vector<float>&& rec, size_t kept, const double stats[5]) {
+  std::lock_guard<std::mutex> lk(ready_mu_);
+  Ready& r = ready_[idx];
+  r.rec = std::move(rec);
+  r.kept = kept;
+  for (int k = 0; k < 5; k++) r.stats[k] = stats[k];
+}
+
 void CCloudOptimization::filter(int idx) {
   const size_t begin = open_begin_, end = xyz.size() / 3;
   pair_index.push_back(idx);
@@ -46,27 +75,36 @@ void CCloudOptimization::filter(int idx) {
   pair_begin.push_back(open_begin_);
   if (!sink_enabled || end <= begin) { kept_per_pair.push_back(0); return; }
   printf("Initial points: %zu\n", end - begin);
-  // CamCenter[idx] = centre of the pair's first camera (:50-51)
-  double cam[3] = {0, 0, 0};
-  if (m_ImageData && idx >= 0 && idx < (int)m_ImageData->cam.size() && !m_ImageData->cam[idx][0].CamCenter.empty())
-    for (int k = 0; k < 3; k++) cam[k] = m_ImageData->cam[idx][0].CamCenter.at<double>(k, 0);
-  std::vector<float> rec(7 * (end - begin));
-  int64_t kept = 0;
+  std::vector<float> rec;
+  size_t kept = 0;
   double stats[5] = {0, 0, 0, 0, 0};
-  const int rc = sb200_sink_filter(sink_device, xyz.data() + 3 * begin, (int64_t)(end - begin), m_sor_meank, m_sor_stdThres, m_mls_radius, cam,
-                                   rec.data(), nullptr, (int64_t)(end - begin), &kept, stats);
-  if (rc != SB200_OK) {
-    last_status = rc;
-    last_error = std::string(sb200_status_string(rc)) + ": " + sb200_sink_last_error();
-    printf("sink filter of pair %d failed: %s\n", idx, last_error.c_str());
-    kept_per_pair.push_back(0);
-    return;
+  bool have = false;
+  {
+    std::lock_guard<std::mutex> lk(ready_mu_);
+    auto it = ready_.find(idx);
+    if (it != ready_.end()) {  // a matcher worker already ran the GPU filter on exactly these points
+      rec = std::move(it->second.rec);
+      kept = it->second.kept;
+      for (int k = 0; k < 5; k++) stats[k] = it->second.stats[k];
+      ready_.erase(it);
+      have = true;
+    }
   }
-  printf("Cloud after filtering: %lld points (mean distance %.6g, stddev %.6g, threshold %.6g; %.2f ms on the GPU)\n", (long long)kept, stats[0],
+  if (!have) {
+    std::string err;
+    if (!FilterPoints(idx, sink_device, xyz.data() + 3 * begin, end - begin, rec, kept, stats, err)) {
+      last_status = SB200_ERR_CUDA;
+      last_error = err;
+      printf("sink filter of pair %d failed: %s\n", idx, last_error.c_str());
+      kept_per_pair.push_back(0);
+      return;
+    }
+  }
+  printf("Cloud after filtering: %zu points (mean distance %.6g, stddev %.6g, threshold %.6g; %.2f ms on the GPU)\n", kept, stats[0],
          stats[1], stats[2], stats[3]);
   normals.insert(normals.end(), rec.begin(), rec.begin() + 7 * kept);  // *cloud_normals += *cloud_normal (:117)
-  kept_per_pair.push_back((size_t)kept);
-  WritePlyPointNormal("tmp/cloud_filter.ply", rec.data(), (size_t)kept);  // :119 (the mesher's input)
+  kept_per_pair.push_back(kept);
+  WritePlyPointNormal("tmp/cloud_filter.ply", rec.data(), kept);  // :119 (the mesher's input)
 }
 
 bool WritePlyPointNormal(const std::string& path, const float* rec7, size_t n) {

@@ -7,6 +7,8 @@
 // stitching: external Windows executables) is out of scope.
 #pragma once
 #include <stdint.h>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -20,6 +22,12 @@ class CCloudOptimization {
   // n InsertPoint calls in one go: xyz = n x 3 f64, bgr = n x 3 u8 (may be null)
   void InsertPoints(const double* xyz, const unsigned char* bgr, size_t n);
   void filter(int idx);  // closes the point range of pair idx (the reference filters + meshes it here)
+  // The GPU part of filter(idx) on its own (thread-safe, const): outlier removal + normals + orientation of n points of pair idx
+  // on `device`.  The matcher's workers call it right after a pair's triangulation — while other pairs are still matching — and
+  // hand the result over with StoreFiltered(); filter(idx) then only appends it (same records, same order, same files).
+  bool FilterPoints(int idx, int device, const double* xyz, size_t n, std::vector<float>& rec7, size_t& kept, double stats5[5],
+                    std::string& err) const;
+  void StoreFiltered(int idx, std::vector<float>&& rec7, size_t kept, const double stats5[5]);
   void run();            // writes <outfilename> (binary little-endian PLY: float xyz, uchar b g r) and <outfilename>.normals.ply
 
   // what the sink holds after the matcher ran
@@ -44,6 +52,9 @@ class CCloudOptimization {
   bool isdelete = false;
   CManageData* m_ImageData = nullptr;
   size_t open_begin_ = 0;
+  struct Ready { std::vector<float> rec; size_t kept = 0; double stats[5] = {0, 0, 0, 0, 0}; };
+  std::map<int, Ready> ready_;  // pairs filtered ahead of filter(idx)
+  std::mutex ready_mu_;
 };
 
 // cloud<idx>.ply as DisparityToCloud writes it when isoutput is set (CStereoMatching.cpp:707-730,753-757)

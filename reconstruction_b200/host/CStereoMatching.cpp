@@ -126,7 +126,7 @@ bool CStereoMatching::Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Qo, sbcv::
   return true;
 }
 
-bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
+bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& r) {
   bool on_device = false;
   if (!Rectify(ctx, CamPair, r.Q, r.Rf, r.Tf, on_device)) {
     r.status = SB200_ERR_BAD_ARG;
@@ -160,6 +160,17 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int CamPair, PairResult& r) {
     sb200_boundary b;
     sb200_get_margin(ctx, m_data->m_PyrmNum - 1, k, &b);
     r.margin[k] = Boundary{b.YL, b.YR, b.XL, b.XR, b.width, b.height};
+  }
+  // the sink's per-pair filter (outlier removal, normals, orientation) on this worker's device, now, while other pairs are
+  // still matching; CCloudOptimization::filter(CamPair) appends the stored result when the pairs are handed over in order
+  if (m_CloudOptimization && m_CloudOptimization->sink_enabled && r.n > 0) {
+    std::vector<float> rec;
+    size_t kept = 0;
+    double stats[5] = {0, 0, 0, 0, 0};
+    std::string err;
+    if (m_CloudOptimization->FilterPoints(CamPair, device, r.xyz.data(), (size_t)r.n, rec, kept, stats, err))
+      m_CloudOptimization->StoreFiltered(CamPair, std::move(rec), kept, stats);
+    // on failure filter(CamPair) retries on the sink's own device and reports
   }
   r.ok = true;
   return true;
@@ -250,7 +261,7 @@ void CStereoMatching::MatchAllLayer() {
   if (G == 1) {
     for (int p = 0; p < P; p++) {
       printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
-      RunPair(ctxs[0], p, results[p]);
+      RunPair(ctxs[0], ctx_dev[0], p, results[p]);
     }
   } else {  // pair p -> context p mod G, context j on device j mod n_dev; each worker owns its context
     std::mutex io;
@@ -259,7 +270,7 @@ void CStereoMatching::MatchAllLayer() {
       workers.emplace_back([&, g]() {
         for (int p = g; p < P; p += G) {
           { std::lock_guard<std::mutex> lk(io); printf("processing pair %d on GPU %d: cam %d and cam %d...\n", p + 1, ctx_dev[g], m_data->cam[p][0].camID, m_data->cam[p][1].camID); }
-          RunPair(ctxs[g], p, results[p]);
+          RunPair(ctxs[g], ctx_dev[g], p, results[p]);
         }
       });
     for (auto& w : workers) w.join();

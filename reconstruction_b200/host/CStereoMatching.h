@@ -39,7 +39,7 @@ class CStereoMatching {
  private:
   struct PairResult;
   bool Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf, bool& staged_on_device);  // :117-168
-  bool RunPair(sb200_ctx* ctx, int CamPair, PairResult& out);
+  bool RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& out);
   sb200_ctx* last_ctx_ = nullptr;
   sbcv::ImagePrefetcher* prefetch_ = nullptr;  // original frames and masks, decoded ahead of the GPU (native Rectify path)
 };
