@@ -7,8 +7,20 @@
 #include <chrono>
 #include <mutex>
 #include <thread>
+#include <utility>
 
 #include "../../include/stereo_b200.h"
+
+// std::allocator that leaves trivially constructible elements uninitialised: the point buffers are sized for the worst case
+// (one point per pixel, 302 MB of doubles at 4096x3072) before the pair is matched; value-initialising them would touch every page
+// (more host time than the GPU spends on the pair), this way only the rows the device copy writes are ever touched.
+template <class T>
+struct UninitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = UninitAllocator<U>; };
+  template <class U, class... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
 
 struct CStereoMatching::PairResult {
   bool ok = false;
@@ -16,8 +28,8 @@ struct CStereoMatching::PairResult {
   std::string error;
   sbcv::Mat Q, Rf, Tf;
   Boundary margin[2];
-  std::vector<double> xyz;
-  std::vector<unsigned char> bgr;
+  std::vector<double, UninitAllocator<double>> xyz;
+  std::vector<unsigned char, UninitAllocator<unsigned char>> bgr;
   int64_t n = 0;
 };
 
