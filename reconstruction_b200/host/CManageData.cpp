@@ -15,9 +15,20 @@ CManageData::~CManageData() {
   }
 }
 
+// The reference's tools write Windows paths ("mask\\0001_Cam0.jpg", BatchProcess/main.cpp:68; filepath "D:\\data\\"): on a
+// system whose separator is '/', backslashes in the file names of a data set are read as separators.
+static std::string native_path(std::string s) {
+#ifndef _WIN32
+  for (char& ch : s)
+    if (ch == '\\') ch = '/';
+#endif
+  return s;
+}
+
 // Keys and order as CManageData::Init (CManageData.cpp:26-76).
 bool CManageData::Init(sbcv::FileStorage fs) {
   fs["filepath"] >> m_FilePath;
+  m_FilePath = native_path(m_FilePath);
   fs["outfilename"] >> outfilename;
   fs["isoutput"] >> isoutput;
   std::string camera_calib_name;
@@ -38,6 +49,9 @@ bool CManageData::Init(sbcv::FileStorage fs) {
   std::vector<std::string> imagelist, masklist;
   fs["imagelist"] >> imagelist;
   fs["masklist"] >> masklist;
+  for (std::string& s : imagelist) s = native_path(s);
+  for (std::string& s : masklist) s = native_path(s);
+  camera_calib_name = native_path(camera_calib_name);
   m_CameraNum = (int)imagelist.size();
 
   sbcv::FileStorage f_calib(m_FilePath + camera_calib_name, sbcv::FileStorage::READ);

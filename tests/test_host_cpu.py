@@ -95,7 +95,7 @@ def test_config_written_like_the_references_batch_tool(cli, tmp_path):
     fs.write("LowestLevelWidth", 160)
     fs.write("LowestLevelHeight", 240)
     fs.write("imagelist", [f"0001_Cam{j}.jpg" for j in range(n_cam)])
-    fs.write("masklist", [f"mask/0001_Cam{j}.jpg" for j in range(n_cam)])
+    fs.write("masklist", [f"mask\\0001_Cam{j}.jpg" for j in range(n_cam)])  # "mask\\" + name, as BatchProcess/main.cpp:68 writes it
     fs.write("camID", np.array([[0, 1], [2, 3], [4, 5], [7, 6]], np.uint8))
     fs.release()
     d = json.loads(subprocess.run([cli, "--dump-config", root + "config.yml"], check=True, capture_output=True, text=True).stdout)
