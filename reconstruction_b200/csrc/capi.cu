@@ -210,11 +210,18 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           std::swap(c->ds[d], c->ds_tmp);
         }
       } else if (stage == SB200_STAGE_ORDER) {
-        for (int d = 0; d < 2; d++) c->launches += launch_order(c->ds[d], W, H, msrc[d], c->st);
+        for (int d = 0; d < 2; d++) {
+          const int n = launch_order(c->ds[d], W, H, msrc[d], c->st);
+          if (n < 0) { c->err = "OrderConstraint: margin wider than the kernel supports"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
+        }
       } else if (stage == SB200_STAGE_UNIQUE_1 || stage == SB200_STAGE_UNIQUE_2) {  // :456-460
-        c->launches += launch_unique_s16(c->ds[0], c->ds[1], W, H, msrc[0], mtgt[0], c->st);
-        c->launches += launch_unique_s16(c->ds[1], c->ds[0], W, H, msrc[1], mtgt[1], c->st);
-        c->launches += launch_unique_s16(c->ds[0], c->ds[1], W, H, msrc[0], mtgt[0], c->st);
+        for (int pass = 0; pass < 3; pass++) {
+          const int a = pass & 1;
+          const int n = launch_unique_s16(c->ds[a], c->ds[1 - a], W, H, msrc[a], mtgt[a], c->st);
+          if (n < 0) { c->err = "UniquenessContraint: margin wider than the kernel supports (16384 px)"; return SB200_ERR_BAD_ARG; }
+          c->launches += n;
+        }
       } else if (stage == SB200_STAGE_REMATCH) {
         int rc = ensure_stats(c, level);
         if (rc) return rc;
@@ -270,9 +277,12 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
     }
     case SB200_STAGE_UNIQUE_3: {
       if (c->elem != 8 || c->dw != W || c->dh != H) { c->err = "stage needs f64 disparity maps of this level"; return SB200_ERR_STATE; }
-      c->launches += launch_unique_f64(c->dd[0], c->dd[1], W, H, msrc[0], mtgt[0], c->st);
-      c->launches += launch_unique_f64(c->dd[1], c->dd[0], W, H, msrc[1], mtgt[1], c->st);
-      c->launches += launch_unique_f64(c->dd[0], c->dd[1], W, H, msrc[0], mtgt[0], c->st);
+      for (int pass = 0; pass < 3; pass++) {
+        const int a = pass & 1;
+        const int n = launch_unique_f64(c->dd[a], c->dd[1 - a], W, H, msrc[a], mtgt[a], c->st);
+        if (n < 0) { c->err = "UniquenessContraint: margin wider than the kernel supports (16384 px)"; return SB200_ERR_BAD_ARG; }
+        c->launches += n;
+      }
       break;
     }
     default:
@@ -330,6 +340,9 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   if (!out) return SB200_ERR_BAD_ARG;
   *out = nullptr;
   if (pyrm_num < 1 || pyrm_num > SB_MAX_LEVELS || lowest_w < 8 || lowest_h < 8 || radius < 1 || radius > 2) return SB200_ERR_BAD_ARG;
+  // widest row the per-row kernels take (k_unique: 512 chunks of 32 px; s16 column indices everywhere); checked here so
+  // that no stage can silently skip its work later
+  if (((long)lowest_w << (pyrm_num - 1)) > 16384 || ((long)lowest_h << (pyrm_num - 1)) > 16384) return SB200_ERR_BAD_ARG;
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) return SB200_ERR_NO_DEVICE;
   cudaDeviceProp prop;

@@ -166,6 +166,10 @@ int launch_order(short* disp, int W, int H, Bound m, cudaStream_t st) {
   (void)H;
   if (m.width <= 0 || m.height <= 0) return 0;
   const size_t smem = (size_t)m.width * 6;
+  if (smem > 48 * 1024) {  // rows wider than 8192 px: opt in to the large carve-out (idempotent; per device)
+    if (smem > 227 * 1024) return -1;
+    cudaFuncSetAttribute(k_order, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  }
   k_order<<<m.height, 256, smem, st>>>(disp, W, m);
   return 1;
 }

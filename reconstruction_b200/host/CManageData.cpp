@@ -74,6 +74,7 @@ bool CManageData::Init(sbcv::FileStorage fs) {
       f_calib["intrinsic-" + currentID] >> c.MatIntrinsics;
       f_calib["extrinsic-" + currentID] >> c.MatExtrinsics;
       if (c.MatIntrinsics.empty() || c.MatExtrinsics.empty() || c.MatExtrinsics.cols != 4 || c.MatExtrinsics.rows != 3 ||
+          c.MatIntrinsics.cols != 3 || c.MatIntrinsics.rows != 3 ||
           c.MatIntrinsics.type() != sbcv::SB_64FC1 || c.MatExtrinsics.type() != sbcv::SB_64FC1) {
         printf("calibration of camera %d missing or malformed\n", c.camID);
         return false;

@@ -45,9 +45,12 @@ struct Huff {
   // canonical decoding tables (ITU T.81 F.2.2.3)
   int mincode[17], maxcode[18], valptr[17];
   uint16_t fast[1 << 11];  // 11-bit look-ahead: (length << 8) | symbol, 0 = longer code
-  void build() {
+  // false: the code-length counts over-subscribe the code space (no prefix code has them; libjpeg's jdhuff.c
+  // refuses such a table too) - building the look-ahead table from it would index past its end
+  bool build() {
     int code = 0, k = 0;
     for (int l = 1; l <= 16; l++) {
+      if (code + bits[l] > (1 << l)) return false;
       valptr[l] = k;
       mincode[l] = code;
       code += bits[l];
@@ -65,6 +68,7 @@ struct Huff {
       }
       code <<= 1;
     }
+    return true;
   }
 };
 
@@ -470,8 +474,8 @@ struct Jpeg {
           if (cnt > 256 || s + cnt > se) { err = "bad DHT"; return false; }
           memcpy(h.vals, s, cnt);
           s += cnt;
+          if (!h.build()) { h.present = false; err = "bad DHT (over-subscribed code lengths)"; return false; }
           h.present = true;
-          h.build();
         }
       } else if (m == 0xC0 || m == 0xC1 || m == 0xC2) {  // SOF0 / SOF1 / SOF2 (progressive)
         progressive = m == 0xC2;
@@ -874,19 +878,39 @@ struct ImagePrefetcher::Impl {
   std::condition_variable cv;
   std::atomic<size_t> next{0};
   std::vector<std::thread> threads;
+  // Bounded look-ahead: at most `window` decoded images wait for their consumers (the reference holds one pair at a
+  // time; a 20-view rig decoded all at once is > 1 GB of host memory).  An entry a consumer is already waiting for is
+  // always decoded (i <= max_wanted), so the bound cannot dead-lock whatever order the consumers ask in.
+  size_t live = 0, window = 16, max_wanted = 0;
+  bool stop = false;  // set by the destructor: consumers are gone, waiting decoders leave
   void work() {
     for (;;) {
       const size_t i = next.fetch_add(1);
       if (i >= entries.size()) return;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&]() { return stop || live < window || i <= max_wanted; });
+        if (stop) return;
+        live++;
+      }
       Mat m;
-      const bool ok = imread(entries[i].path, m, entries[i].gray);
-      const std::string e = ok ? std::string() : imread_error();
+      bool ok = false;
+      std::string e;
+      try {
+        ok = imread(entries[i].path, m, entries[i].gray);
+        if (!ok) e = imread_error();
+      } catch (const std::exception& ex) {  // e.g. std::bad_alloc: reported through get(), never terminates the process
+        ok = false;
+        m.release();
+        e = std::string("decoding ") + entries[i].path + ": " + ex.what();
+      }
       {
         std::lock_guard<std::mutex> lk(mu);
         entries[i].img = m;
         entries[i].ok = ok;
         entries[i].err = e;
         entries[i].done = true;
+        if (!ok || entries[i].users <= 0) live--;
       }
       cv.notify_all();
     }
@@ -895,6 +919,11 @@ struct ImagePrefetcher::Impl {
 
 ImagePrefetcher::ImagePrefetcher() : impl_(new Impl) {}
 ImagePrefetcher::~ImagePrefetcher() {
+  {
+    std::lock_guard<std::mutex> lk(impl_->mu);
+    impl_->stop = true;
+  }
+  impl_->cv.notify_all();
   for (std::thread& t : impl_->threads) t.join();
   delete impl_;
 }
@@ -915,7 +944,11 @@ void ImagePrefetcher::start(const std::vector<std::pair<std::string, bool>>& req
       impl_->entries[it->second].users++;
     }
   }
+  if (const char* e = getenv("SB200_DECODE_WINDOW")) {
+    if (atoi(e) > 0) impl_->window = (size_t)atoi(e);
+  }
   if (n_threads < 1) n_threads = 1;
+  if (impl_->window < (size_t)n_threads) impl_->window = (size_t)n_threads;
   if ((size_t)n_threads > impl_->entries.size()) n_threads = (int)impl_->entries.size();
   for (int t = 0; t < n_threads; t++) impl_->threads.emplace_back([this]() { impl_->work(); });
 }
@@ -929,11 +962,19 @@ bool ImagePrefetcher::get(const std::string& path, bool grayscale, Mat& out, std
   }
   std::unique_lock<std::mutex> lk(impl_->mu);
   Impl::Entry& e = impl_->entries[it->second];
+  if (it->second > impl_->max_wanted) {
+    impl_->max_wanted = it->second;
+    impl_->cv.notify_all();
+  }
   impl_->cv.wait(lk, [&]() { return e.done; });
   if (err) *err = e.err;
   const bool ok = e.ok;
   if (ok) out = e.img;
-  if (--e.users <= 0) e.img.release();  // last consumer: the cache lets go of the pixels
+  if (--e.users == 0 && ok) {  // last consumer: the cache lets go of the pixels and a decoder may run further ahead
+    e.img.release();
+    impl_->live--;
+    impl_->cv.notify_all();
+  }
   return ok;
 }
 

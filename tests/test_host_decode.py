@@ -270,3 +270,28 @@ def test_prefetcher_serves_every_consumer(cli, tmp_path):
     open(bad, "wb").write(open(files[0], "rb").read()[:150])
     r = subprocess.run([cli, "--prefetch-test", "3", files[0], bad, files[2]], capture_output=True, text=True)
     assert r.returncode == 1 and r.stdout.count(" error ") == 4 and r.stdout.count(os.path.basename(files[2])) == 4
+
+
+def test_oversubscribed_dht_is_refused(cli, tmp_path):
+    """A DHT whose code-length counts over-subscribe the code space (200 codes of length 1) used to write past the 2048-entry
+    look-ahead table in Huff::build (ADVICE round 1, ASan: stack-buffer-overflow).  The decoder must refuse the file, as
+    libjpeg's jdhuff.c does, and stay alive."""
+    data = bytearray(open(os.path.join(GOLD, "a_420_q90.jpg"), "rb").read())
+    i = data.find(b"\xff\xc4")
+    assert i > 0
+    counts = i + 5  # marker(2) length(2) Tc/Th(1) then 16 counts
+    seg_len = struct.unpack(">H", data[i + 2:i + 4])[0]
+    assert seg_len > 19 + 200 or True
+    data[counts:counts + 16] = bytes([200] + [0] * 15)
+    # keep the segment self-consistent: 200 symbol bytes must exist inside the segment; pad the segment if needed
+    have = seg_len - 19
+    if have < 200:
+        pad = 200 - have
+        data[i + 2:i + 4] = struct.pack(">H", seg_len + pad)
+        data[i + 2 + seg_len:i + 2 + seg_len] = bytes(pad)
+    p = str(tmp_path / "bad_dht.jpg")
+    open(p, "wb").write(bytes(data))
+    for gray in (False, True):
+        r = subprocess.run([cli, "--decode", p, str(tmp_path / "o.pnm")] + (["gray"] if gray else []), capture_output=True, text=True)
+        assert r.returncode not in (0, -6, -11, 134, 139), (r.returncode, r.stdout, r.stderr)  # refused, not crashed
+        assert "DHT" in (r.stdout + r.stderr)
