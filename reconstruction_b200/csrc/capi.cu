@@ -54,6 +54,7 @@ struct sb200_ctx {
   int stats_level = -1;
   // refinement: per-direction table / code / miss list (rs[0] also owns the counters)
   RefineScratch rs[2]{};
+  bool refine_tma = true;                 // SB200_REFINE_TMA=0: plain loads in the tile load phase
   int refine_T = 5, refine_variant = -1;  // sweeps fused per launch, tile shape (< 0: per level); SB200_REFINE_T / _TILE
   // triangulation
   CloudScratch cs{};
@@ -262,7 +263,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           c->events.push_back(ev);
         }
         double* res[2] = {nullptr, nullptr};
-        const int n = launch_refine_fused(pv, msrc, in, it, c->ws, c->refine_T, c->refine_variant, s, res, c->st);
+        const int n = launch_refine_fused(pv, msrc, in, it, c->ws, c->refine_T, c->refine_variant, c->refine_tma ? 1 : 0, s, res, c->st);
         if (n < 0) { c->err = "too many refinement sweeps"; return SB200_ERR_BAD_ARG; }
         c->launches += n;
         for (int d = 0; d < 2; d++) {
@@ -403,6 +404,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   if (const char* e = getenv("SB200_REFINE_T")) c->refine_T = atoi(e) > 0 ? atoi(e) : c->refine_T;
   if (const char* e = getenv("SB200_REFINE_TILE")) c->refine_variant = atoi(e);
   if (c->refine_variant > 7) c->refine_variant = -1;
+  if (const char* e = getenv("SB200_REFINE_TMA")) c->refine_tma = atoi(e) != 0;
   CK(dalloc(&c->cs.run, n + pad));
   CK(dalloc(&c->cs.eroded, n + pad));
   CK(dalloc(&c->cs.row_count, (size_t)c->lv[pyrm_num - 1].h + 2));

@@ -91,8 +91,9 @@ struct RefineFusedArgs {
 };
 // variant: tile shape / table access, see k_refine_dims in refine.cu; < 0 = pick per level.
 // s[d].A / s[d].B / table / code / miss_* are per direction; s[0].ev_begin/ev_end bracket the sweeps.
+// allow_tma: tile load phase through cp.async.bulk.tensor where the level's pitch permits it (SB200_REFINE_TMA=0 turns it off)
 int launch_refine_fused(const PairViews v[2], const Bound ms[2], short* const in[2], int iterations, double ws, int T,
-                        int variant, const RefineScratch s[2], double* result[2], cudaStream_t st);
+                        int variant, int allow_tma, const RefineScratch s[2], double* result[2], cudaStream_t st);
 
 // K10 DisparityToCloud<double> (:682-761)
 struct CloudScratch {
