@@ -51,6 +51,7 @@ struct sb200_ctx {
   unsigned* search_n = nullptr;
   SearchScratch ss{};
   bool screen = true;                             // SB200_SCREEN=0 disables the integer screening pass
+  bool band = true;                               // SB200_BAND=0: K3 through the register-resident screening kernel instead of ncc_band.cu
   int stats_level = -1;
   // refinement: per-direction table / code / miss list (rs[0] also owns the counters)
   RefineScratch rs[2]{};
@@ -174,8 +175,11 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
   const Bound msrc[2] = {m0, m1}, mtgt[2] = {m1, m0};
   switch (stage) {
     case SB200_STAGE_INITIAL_MATCH: {
-      int rc = ensure_stats(c, level);
-      if (rc) return rc;
+      const bool band = c->band && c->screen && c->R == 2 && c->offset == 2 && level > 0 && l.w % 16 == 0;
+      if (!band) {  // the band kernel forms its window sums itself; every other search reads the per-level statistics map
+        int rc = ensure_stats(c, level);
+        if (rc) return rc;
+      }
       if (level == 0) {
         for (int d = 0; d < 2; d++) {
           const int n = launch_lowest_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, c->st);
@@ -189,7 +193,7 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
         }
         for (int d = 0; d < 2; d++) {
           const int n = launch_high_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->offset, c->dd[d], c->dw,
-                                          c->dh, c->range_lo, c->range_hi, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, c->st);
+                                          c->dh, c->range_lo, c->range_hi, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, band, c->st);
           if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
           c->launches += n;
         }
@@ -386,6 +390,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   c->ss.list = c->search_list; c->ss.list2 = c->search_list2; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
   CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
+  if (const char* e = getenv("SB200_BAND")) c->band = atoi(e) != 0;
   CK(dalloc(&c->ds_tmp, n + pad));
   CK(dalloc(&c->range_lo, n + pad));
   CK(dalloc(&c->range_hi, n + pad));

@@ -33,8 +33,14 @@ int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStr
 // K2  LowestLevelInitialMatch (:170-227)
 int launch_lowest_match(const PairViews& v, Bound ms, Bound mt, int R, short* out, const SearchScratch* sc, cudaStream_t st);
 // K3  HighLevelInitialMatch (:231-308): prev = refined f64 map of the coarser level (pw x ph)
+// band: take the TMA / shared-memory band kernel (ncc_band.cu) where the level allows it (needs sc, R == 2, offset == 2)
 int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
-                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, cudaStream_t st);
+                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, bool band, cudaStream_t st);
+// K3 band path (ncc_band.cu): NOMATCH fill, hole ranges, the band kernel; leaves the undecided pixels in sc->list with their
+// ranges in lo_map / hi_map.  -2: the level cannot take this path.
+int launch_high_match_band(const PairViews& v, Bound ms, Bound mt, int offset, const double* prev, int pw, int ph, short* lo_map,
+                           short* hi_map, short* out, const SearchScratch* sc, cudaStream_t st);
+int launch_range_lists(const PairViews& v, const short* lo_map, const short* hi_map, short* disp, const SearchScratch* sc, cudaStream_t st);
 // K4  SmoothConstraint (:370-448): in -> out (out-of-place gather formulation)
 int launch_smooth(const short* in, short* out, int W, int H, Bound m, cudaStream_t st);
 // K5  OrderConstraint (:310-368): in place

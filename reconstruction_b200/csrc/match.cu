@@ -253,7 +253,9 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
 // The same screening for ranges of any width (full-range search of the lowest level, hole look-ahead and Rematch ranges):
 // one warp per listed pixel, lanes stride the candidates, (best, second best) merged across the warp.  Settles a pixel
 // under the same margin rule as k_ncc_screen5; the rest goes to `out_list` for the exact pass.
-template <int MODE>
+// ONFLY: the window sums (sum, sum of squares) are formed from the window words on the spot instead of being read from
+// the per-level statistics map (K3's band path does not build that map).
+template <int MODE, bool ONFLY>
 __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsigned* __restrict__ list, const unsigned* __restrict__ n_ptr,
                                                          unsigned cap, const short* __restrict__ lo_map, const short* __restrict__ hi_map,
                                                          int lo_const, int hi_const, short* __restrict__ disp,
@@ -265,22 +267,38 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
     const long f = list[e];
     const int y = (int)(f / W), x = (int)(f - (long)y * W);
     const int lo = lo_map ? (int)lo_map[f] : lo_const, hi = lo_map ? (int)hi_map[f] : hi_const;
-    const int2 sl = v.istat0[f];
-    const int varL = 75 * sl.y - sl.x * sl.x;
-    bool bad = varL == 0 || lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || hi < lo;  // warp-uniform
+    bool bad = lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || hi < lo;  // warp-uniform
+    int2 sl = make_int2(0, 0);
+    int varL = 0;
     float best = -3.0e38f, second = -3.0e38f;
     int bi = -1, nvalid = 0;
+    unsigned L[5][4];
     if (!bad) {
-      unsigned L[5][4];
 #pragma unroll
       for (int r = 0; r < 5; r++) {
         load_row_words<4>(v.img0, ((long)(y - 2 + r) * W + (x - 2)) * 3, L[r]);
         L[r][3] &= 0x00ffffffu;
       }
+      if (ONFLY) {
+#pragma unroll
+        for (int r = 0; r < 5; r++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            sl.x = (int)__dp4a(L[r][i], 0x01010101u, (unsigned)sl.x);
+            sl.y = (int)__dp4a(L[r][i], L[r][i], (unsigned)sl.y);
+          }
+      } else {
+        sl = v.istat0[f];
+      }
+      varL = 75 * sl.y - sl.x * sl.x;
+      bad = varL == 0;
+    }
+    if (!bad) {
       for (int im = lo + lane; im <= hi; im += 32) {
         const long ft = (long)y * W + im;
         if (v.mask1[ft] != 255) continue;
-        const int2 sr = v.istat1[ft];
+        int2 sr = make_int2(0, 0);
+        if (!ONFLY) sr = v.istat1[ft];
         unsigned slr = 0;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
@@ -288,6 +306,14 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
           load_row_words<4>(v.img1, ((long)(y - 2 + r) * W + (im - 2)) * 3, q);
 #pragma unroll
           for (int i = 0; i < 4; i++) slr = __dp4a(L[r][i], q[i], slr);
+          if (ONFLY) {
+            q[3] &= 0x00ffffffu;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              sr.x = (int)__dp4a(q[i], 0x01010101u, (unsigned)sr.x);
+              sr.y = (int)__dp4a(q[i], q[i], (unsigned)sr.y);
+            }
+          }
         }
         const int num = 75 * (int)slr - sl.x * sr.x;
         const int varR = 75 * sr.y - sr.x * sr.x;
@@ -346,7 +372,7 @@ static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, 
       dim3 gs((ms.width + 127) / 128, ms.height);
       k_ncc_screen5<MODE><<<gs, 128, 0, st>>>(v, ms, lo_map, hi_map, disp, sc->list, sc->n_list, sc->cap);
     }
-    k_ncc_screen_wide<MODE><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, lo, hi, disp, sc->list2, sc->n_list + 1);
+    k_ncc_screen_wide<MODE, false><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, lo, hi, disp, sc->list2, sc->n_list + 1);
     k_ncc_search_list<5, 32><<<148 * 4, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, lo, hi, disp);
     k_count_add<<<1, 1, 0, st>>>(sc->n_list + 1, sc->counters + 1);
     return 4;
@@ -434,8 +460,11 @@ __global__ void __launch_bounds__(128) k_high_ranges(const uint8_t* __restrict__
 }
 
 int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset, const double* prev, int pw, int ph,
-                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, cudaStream_t st) {
-  (void)ph;
+                      short* lo_scratch, short* hi_scratch, short* out, const SearchScratch* sc, bool band, cudaStream_t st) {
+  if (R == 2 && sc && band) {  // TMA / shared-memory band kernel; falls through where the level cannot take it
+    const int nb = launch_high_match_band(v, ms, mt, offset, prev, pw, ph, lo_scratch, hi_scratch, out, sc, st);
+    if (nb >= 0) return (ms.width <= 0 || ms.height <= 0) ? nb : nb + launch_range_lists(v, lo_scratch, hi_scratch, out, sc, st);
+  }
   int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
   if (ms.width <= 0 || ms.height <= 0) return n;
   const int warps = 4;
@@ -449,4 +478,14 @@ int launch_high_match(const PairViews& v, Bound ms, Bound mt, int R, int offset,
 int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, const short* BR, short* disp,
                           const SearchScratch* sc, cudaStream_t st) {
   return search_dispatch<8, SEARCH_REMATCH>(v, ms, R, 0, 0, BL, BR, disp, sc, st);
+}
+
+// The two list kernels on a pixel list that is already filled (K3's band path, ncc_band.cu): any-width integer screening with the
+// window sums formed on the spot, then the exact pass for what is left (eight lanes per pixel: the ranges are narrow).
+int launch_range_lists(const PairViews& v, const short* lo_map, const short* hi_map, short* disp, const SearchScratch* sc, cudaStream_t st) {
+  k_ncc_screen_wide<SEARCH_RANGE_MAPS, true><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, 0, 0, disp, sc->list2,
+                                                                    sc->n_list + 1);
+  k_ncc_search_list<5, 8><<<148 * 2, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, 0, 0, disp);
+  k_count_add<<<1, 1, 0, st>>>(sc->n_list + 1, sc->counters + 1);
+  return 3;
 }

@@ -154,11 +154,27 @@ int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStr
   return 1;
 }
 
-__global__ void k_fill_s16(short* p, long n, short v) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+// 16-byte stores over the aligned body, scalar stores at the two ends (the maps come from cudaMalloc: the head is empty)
+__global__ void __launch_bounds__(256) k_fill_s16(short* p, long n, short v) {
+  const unsigned vv = (unsigned)(unsigned short)v * 0x00010001u;
+  long head = (long)(((16 - ((size_t)p & 15)) & 15) / 2);
+  if (head > n) head = n;
+  const long body = (n - head) / 8;
+  uint4* q = reinterpret_cast<uint4*>(p + head);
+  const uint4 w = make_uint4(vv, vv, vv, vv);
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < body; i += (long)gridDim.x * blockDim.x) q[i] = w;
+  if (blockIdx.x == 0) {
+    if ((long)threadIdx.x < head) p[threadIdx.x] = v;
+    const long t = head + body * 8 + threadIdx.x;
+    if (t < n) p[t] = v;  // at most 7 trailing elements
+  }
 }
 int launch_fill_s16(short* p, long n, short v, cudaStream_t st) {
-  k_fill_s16<<<(int)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+  if (n <= 0) return 0;
+  const long body = n / 8;
+  int blocks = (int)((body + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  k_fill_s16<<<blocks, 256, 0, st>>>(p, n, v);
   return 1;
 }
