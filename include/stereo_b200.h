@@ -183,6 +183,10 @@ SB200_API int sb200_get_refine_profile(sb200_ctx* ctx, int level, double* sweep_
 /* Counters: [0] = pixels the integer screening pass of the NCC searches left to the exact FP64 search (near ties,
  * flat windows, wide ranges), [1] = out-of-table pixel evaluations of the refinement kernel. */
 SB200_API int sb200_get_refine_counters(sb200_ctx* ctx, int64_t* out2, int reset);
+/* NCC searches (CStereoMatching.cpp:202-218, :268-300, :535-562): [0] = pixels the tile kernel of HighLevelInitialMatch handed to the
+ * list kernels (holes with a carried range, near ties, target strips outside the staged box), [1] = pixels that reached the exact
+ * FP64 pass. */
+SB200_API int sb200_get_search_counters(sb200_ctx* ctx, int64_t* out2, int reset);
 
 /* ---- the sink's per-pair filter, on the device (next row f-3) ---------------------------------------
  * What CCloudOptimization::filter(idx) does to the points InsertPoint collected for one camera pair before it meshes them
@@ -197,6 +201,38 @@ SB200_API int sb200_sink_filter(int device, const double* xyz, int64_t n, int so
                                 const double* cam_center, float* out_xyz_normal_curv, int32_t* kept_index, int64_t capacity,
                                 int64_t* n_kept, double* stats5);
 SB200_API const char* sb200_sink_last_error(void);
+
+/* ---- the exchange step: per-pair point buffers gathered on every rank ------------------------
+ * The reference processes the camera pairs serially in one process (CStereoMatching.cpp:17-33) and appends every pair's cloud
+ * to the sink in pair order (CloudOptimization/CCloudOptimization.cpp:123).  Here the pairs shard one per GPU; after
+ * DisparityToCloud every rank contributes its pair's points and receives everybody's, rank-major (= pair order), not padded:
+ * one NCCL all-gather of the counts, then one grouped collective in which each rank broadcasts its own xyz / bgr / pix block.
+ * One communicator per GPU: one process per GPU (the unique id travels over the launcher's own bootstrap) or one host thread
+ * per GPU inside a process.  NCCL is bound at run time (libnccl.so.2); without it these calls return SB200_ERR_NO_DEVICE and
+ * sb200_comm_last_error(NULL) says why.  `producers` = contexts per rank that submit pairs (1 for the synchronous call),
+ * `slots` = snapshots a producer may have waiting for the exchange (2). */
+#define SB200_UNIQUE_ID_BYTES 128
+typedef struct sb200_comm sb200_comm;
+SB200_API int sb200_comm_unique_id(void* id_out /* SB200_UNIQUE_ID_BYTES, call on one rank and distribute */);
+SB200_API int sb200_comm_init(sb200_comm** out, int device, int rank, int nranks, const void* unique_id, int producers, int slots);
+SB200_API void sb200_comm_destroy(sb200_comm* comm);
+SB200_API const char* sb200_comm_last_error(const sb200_comm* comm);
+/* Synchronous form: gathers the points of `ctx`'s last triangulation from every rank.  counts_out[nranks]; the host buffers
+ * (any may be NULL) receive the rank-major concatenation and must hold `capacity` points; total_out = sum of the counts. */
+SB200_API int sb200_allgather_points(sb200_comm* comm, sb200_ctx* ctx, int64_t* counts_out, double* xyz_host, uint8_t* bgr_host,
+                                     int32_t* pix_host, int64_t capacity, int64_t* total_out);
+/* Overlapped form.  submit: snapshot ctx's points on ctx's own stream and return at once; an exchange thread issues the
+ * collectives in ticket order (ticket = seq * producers + producer, the same sequence on every rank) on its own low-priority
+ * stream, so a context never waits for another rank and runs up to `slots` pairs ahead.  wait: block until `ticket` is gathered
+ * (optionally copy it to host buffers); the two most recent results stay on the device (sb200_exchange_device).  drain: wait
+ * until tickets [0, n_tickets) are gathered and the exchange stream is idle. */
+SB200_API int sb200_exchange_submit(sb200_comm* comm, sb200_ctx* ctx, int producer, int64_t seq);
+SB200_API int sb200_exchange_wait(sb200_comm* comm, int64_t ticket, int64_t* counts_out, double* xyz_host, uint8_t* bgr_host,
+                                  int32_t* pix_host, int64_t capacity, int64_t* total_out);
+SB200_API int sb200_exchange_device(sb200_comm* comm, int64_t ticket, void** xyz_dev, void** bgr_dev, void** pix_dev, int64_t* total);
+SB200_API int sb200_exchange_drain(sb200_comm* comm, int64_t n_tickets);
+/* Device time spent inside the collectives (CUDA events on the exchange stream), bytes received, exchanges done. */
+SB200_API int sb200_comm_stats(sb200_comm* comm, double* collective_ms, int64_t* bytes_received, int64_t* n_exchanges, int reset);
 
 /* glibc-compatible exp() used by the refinement weights (see DESIGN.md "exp"); host twin of the
  * device function, exported so the CPU tests can pin it against the C library. */

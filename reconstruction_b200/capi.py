@@ -29,12 +29,15 @@ SYMBOLS = [
     "sb200_disparity_info", "sb200_get_disparity", "sb200_set_disparity", "sb200_get_rematch_bounds", "sb200_get_level",
     "sb200_get_margin", "sb200_triangulate", "sb200_get_points", "sb200_points_device", "sb200_match_pair_host",
     "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
-    "sb200_get_refine_profile", "sb200_get_stage_level_ms",
+    "sb200_get_refine_profile", "sb200_get_stage_level_ms", "sb200_get_search_counters",
     "sb200_exp_host",
     "sb200_rectify_calib", "sb200_stereo_rectify_host", "sb200_rectify_view", "sb200_pair_build", "sb200_get_rectify_maps",
     "sb200_set_rectify_maps", "sb200_get_remapped_mask",
     "sb200_sink_filter", "sb200_sink_last_error",
+    "sb200_comm_unique_id", "sb200_comm_init", "sb200_comm_destroy", "sb200_comm_last_error", "sb200_allgather_points",
+    "sb200_exchange_submit", "sb200_exchange_wait", "sb200_exchange_device", "sb200_exchange_drain", "sb200_comm_stats",
 ]
+UNIQUE_ID_BYTES = 128
 
 
 class StereoError(RuntimeError):
@@ -91,6 +94,7 @@ def load():
         "sb200_set_profiling": (i32, [vp, i32]),
         "sb200_get_stage_ms": (i32, [vp, vp, i32]),
         "sb200_get_refine_counters": (i32, [vp, vp, i32]),
+        "sb200_get_search_counters": (i32, [vp, vp, i32]),
         "sb200_get_refine_profile": (i32, [vp, i32, P(dbl), P(i64), P(i64), i32]),
         "sb200_get_stage_level_ms": (i32, [vp, i32, i32, P(dbl), i32]),
         "sb200_exp_host": (dbl, [dbl]),
@@ -103,6 +107,16 @@ def load():
         "sb200_get_remapped_mask": (i32, [vp, vp]),
         "sb200_sink_filter": (i32, [i32, vp, i64, i32, dbl, dbl, vp, vp, vp, i64, P(i64), vp]),
         "sb200_sink_last_error": (C.c_char_p, []),
+        "sb200_comm_unique_id": (i32, [vp]),
+        "sb200_comm_init": (i32, [P(vp), i32, i32, i32, vp, i32, i32]),
+        "sb200_comm_destroy": (None, [vp]),
+        "sb200_comm_last_error": (C.c_char_p, [vp]),
+        "sb200_allgather_points": (i32, [vp, vp, vp, vp, vp, vp, i64, P(i64)]),
+        "sb200_exchange_submit": (i32, [vp, vp, i32, i64]),
+        "sb200_exchange_wait": (i32, [vp, i64, vp, vp, vp, vp, i64, P(i64)]),
+        "sb200_exchange_device": (i32, [vp, i64, P(vp), P(vp), P(vp), P(i64)]),
+        "sb200_exchange_drain": (i32, [vp, i64]),
+        "sb200_comm_stats": (i32, [vp, P(dbl), P(i64), P(i64), i32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -308,6 +322,12 @@ class StereoB200:
         self._ck(self.lib.sb200_get_refine_profile(self.h, level, C.byref(ms), C.byref(n), C.byref(px), int(reset)), "get_refine_profile")
         return ms.value, n.value, px.value
 
+    def search_counters(self, reset=True):
+        """(pixels handed to the list kernels by the K3 tile kernel, pixels that reached the exact FP64 pass)"""
+        out = np.zeros(2, np.int64)
+        self._ck(self.lib.sb200_get_search_counters(self.h, _p(out), int(reset)), "get_search_counters")
+        return out
+
     def refine_counters(self, reset=True):
         out = np.zeros(2, np.int64)
         self._ck(self.lib.sb200_get_refine_counters(self.h, _p(out), int(reset)), "get_refine_counters")
@@ -357,3 +377,83 @@ def sink_filter(xyz, sor_meank, sor_std_mul, normal_radius, cam_center, device=0
         raise StereoError(f"sink_filter: {lib.sb200_status_string(rc).decode()} - {lib.sb200_sink_last_error().decode()}")
     return out[:m.value].copy(), kept[:m.value].copy(), {"mean": stats[0], "stddev": stats[1], "threshold": stats[2], "device_ms": stats[3],
                                                         "widened_queries": int(stats[4])}
+
+
+def comm_unique_id() -> bytes:
+    """NCCL unique id (call on one rank, hand the bytes to the others over the launcher's bootstrap)."""
+    buf = C.create_string_buffer(UNIQUE_ID_BYTES)
+    lib = load()
+    rc = lib.sb200_comm_unique_id(buf)
+    if rc != 0:
+        raise StereoError(f"comm_unique_id: {lib.sb200_status_string(rc).decode()} - {lib.sb200_comm_last_error(None).decode()}")
+    return buf.raw
+
+
+class PointComm:
+    """The exchange step behind the C ABI (sb200_comm_*): one communicator per GPU."""
+
+    def __init__(self, device, rank, nranks, unique_id: bytes, producers=1, slots=2):
+        self.lib = load()
+        self.rank, self.nranks, self.producers = rank, nranks, producers
+        self.h = C.c_void_p()
+        idb = C.create_string_buffer(unique_id, UNIQUE_ID_BYTES)
+        rc = self.lib.sb200_comm_init(C.byref(self.h), device, rank, nranks, idb, producers, slots)
+        if rc != 0:
+            msg = self.lib.sb200_comm_last_error(self.h).decode()
+            if self.h:
+                self.lib.sb200_comm_destroy(self.h)
+                self.h = None
+            raise StereoError(f"sb200_comm_init: {self.lib.sb200_status_string(rc).decode()} - {msg}")
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise StereoError(f"{what}: {self.lib.sb200_status_string(rc).decode()} - {self.lib.sb200_comm_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sb200_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def allgather_points(self, ctx: StereoB200, capacity: int, want_host=True):
+        """Synchronous gather of ctx's points from every rank: (counts [nranks], xyz, bgr, pix) in rank-major order."""
+        counts = np.zeros(self.nranks, np.int64)
+        total = C.c_int64()
+        if want_host:
+            xyz, bgr, pix = np.empty((capacity, 3)), np.empty((capacity, 3), np.uint8), np.empty(capacity, np.int32)
+        else:
+            xyz = bgr = pix = None
+        self._ck(self.lib.sb200_allgather_points(self.h, ctx.h, _p(counts), _p(xyz), _p(bgr), _p(pix), capacity, C.byref(total)), "allgather_points")
+        n = total.value
+        if not want_host:
+            return counts, None, None, None
+        return counts, xyz[:n], bgr[:n], pix[:n]
+
+    def submit(self, ctx: StereoB200, producer: int, seq: int):
+        self._ck(self.lib.sb200_exchange_submit(self.h, ctx.h, producer, seq), "exchange_submit")
+
+    def wait(self, ticket: int, capacity: int = 0, want_host=False):
+        counts = np.zeros(self.nranks, np.int64)
+        total = C.c_int64()
+        if want_host:
+            xyz, bgr, pix = np.empty((capacity, 3)), np.empty((capacity, 3), np.uint8), np.empty(capacity, np.int32)
+        else:
+            xyz = bgr = pix = None
+        self._ck(self.lib.sb200_exchange_wait(self.h, ticket, _p(counts), _p(xyz), _p(bgr), _p(pix), capacity, C.byref(total)), "exchange_wait")
+        n = total.value
+        if not want_host:
+            return counts, n
+        return counts, xyz[:n], bgr[:n], pix[:n]
+
+    def drain(self, n_tickets: int):
+        self._ck(self.lib.sb200_exchange_drain(self.h, n_tickets), "exchange_drain")
+
+    def stats(self, reset=True):
+        ms, nb, nx = C.c_double(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.sb200_comm_stats(self.h, C.byref(ms), C.byref(nb), C.byref(nx), int(reset)), "comm_stats")
+        return {"collective_ms": ms.value, "bytes_received": nb.value, "exchanges": nx.value}

@@ -31,6 +31,8 @@ struct sb200_ctx {
   int device = 0, L = 0, W0 = 0, H0 = 0, OW = 0, OH = 0, R = 2, offset = 2, refine_override = -1;
   double ws = 0.5;
   cudaStream_t st = nullptr;
+  cudaStream_t side = nullptr;  // forked from st for kernels that run beside the main one of a stage (hole ranges of K3)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::vector<Level> lv;
   int* d_margins = nullptr;  // [L][2][4]
   bool uploaded = false, calib_set = false;
@@ -388,6 +390,10 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(dalloc(&c->search_list2, n + pad));
   CK(dalloc(&c->search_n, 2));
   c->ss.list = c->search_list; c->ss.list2 = c->search_list2; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
+  CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  c->ss.side = c->side; c->ss.ev_fork = c->ev_fork; c->ss.ev_join = c->ev_join;
   CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
   if (const char* e = getenv("SB200_BAND")) c->band = atoi(e) != 0;
@@ -450,6 +456,9 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaFree(c->rc_src_img); cudaFree(c->rc_src_mask); cudaFree(c->rc_tab); cudaFree(c->rc_map1); cudaFree(c->rc_map2); cudaFree(c->rc_ellipse);
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
   if (c->h_npoints) cudaFreeHost(c->h_npoints);
+  if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+  if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->st) cudaStreamDestroy(c->st);
   delete c;
 }
@@ -861,6 +870,18 @@ int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
   if (reset) CK(cudaMemset(c->rs[0].counters, 0, sizeof h));
   CK(cudaMemcpy(h, c->search_counters, sizeof h, cudaMemcpyDeviceToHost));
   out2[0] = (int64_t)h[1];
+  if (reset) CK(cudaMemset(c->search_counters, 0, sizeof h));
+  return SB200_OK;
+}
+
+int sb200_get_search_counters(sb200_ctx* c, int64_t* out2, int reset) {
+  if (!c || !out2) return SB200_ERR_BAD_ARG;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->st));
+  unsigned long long h[2];
+  CK(cudaMemcpy(h, c->search_counters, sizeof h, cudaMemcpyDeviceToHost));
+  out2[0] = (int64_t)h[0];
+  out2[1] = (int64_t)h[1];
   if (reset) CK(cudaMemset(c->search_counters, 0, sizeof h));
   return SB200_OK;
 }

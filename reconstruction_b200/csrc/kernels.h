@@ -25,7 +25,9 @@ struct SearchScratch {
   unsigned* list2;               // ... left by the per-warp screening pass: input of the exact pass
   unsigned* n_list;              // device counters [2] of the current search
   unsigned cap;
-  unsigned long long* counters;  // [2]: [1] += n_list after every search (instrumentation)
+  unsigned long long* counters;  // [2]: [0] += pixels listed, [1] += pixels left to the exact pass, after every search (instrumentation)
+  cudaStream_t side;             // optional second stream (+ fork / join events) for work that runs beside the main kernel
+  cudaEvent_t ev_fork, ev_join;
 };
 // integer-only (sum, sum of squares) map of the 5x5x3 windows
 int launch_window_istats(const uint8_t* img, int W, int H, int2* istats, cudaStream_t st);

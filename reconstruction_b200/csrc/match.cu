@@ -251,23 +251,26 @@ __global__ void __launch_bounds__(128) k_ncc_screen5(PairViews v, Bound ms, cons
 }
 
 // The same screening for ranges of any width (full-range search of the lowest level, hole look-ahead and Rematch ranges):
-// one warp per listed pixel, lanes stride the candidates, (best, second best) merged across the warp.  Settles a pixel
-// under the same margin rule as k_ncc_screen5; the rest goes to `out_list` for the exact pass.
+// G lanes per listed pixel (32 / G pixels per warp), the lanes of a group stride the candidates, (best, second best) merged
+// across the group.  Settles a pixel under the same margin rule as k_ncc_screen5; the rest goes to `out_list` for the exact pass.
 // ONFLY: the window sums (sum, sum of squares) are formed from the window words on the spot instead of being read from
 // the per-level statistics map (K3's band path does not build that map).
-template <int MODE, bool ONFLY>
+template <int MODE, bool ONFLY, int G>
 __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsigned* __restrict__ list, const unsigned* __restrict__ n_ptr,
                                                          unsigned cap, const short* __restrict__ lo_map, const short* __restrict__ hi_map,
                                                          int lo_const, int hi_const, short* __restrict__ disp,
                                                          unsigned* __restrict__ out_list, unsigned* __restrict__ n_out) {
-  const int W = v.W, lane = threadIdx.x & 31;
+  constexpr int PPW = 32 / G;  // pixels per warp
+  const int W = v.W, lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
   const unsigned n = min(*n_ptr, cap);
   const unsigned nwarp = gridDim.x * (blockDim.x >> 5);
-  for (unsigned e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += nwarp) {
-    const long f = list[e];
+  for (unsigned e0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * PPW; e0 < n; e0 += nwarp * PPW) {
+    const unsigned e = e0 + grp;
+    const bool have = e < n;
+    const long f = have ? list[e] : 0;
     const int y = (int)(f / W), x = (int)(f - (long)y * W);
     const int lo = lo_map ? (int)lo_map[f] : lo_const, hi = lo_map ? (int)hi_map[f] : hi_const;
-    bool bad = lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || hi < lo;  // warp-uniform
+    bool bad = !have || lo < 2 || hi > W - 3 || x < 2 || x > W - 3 || y < 2 || y > v.H - 3 || hi < lo;  // uniform over the group
     int2 sl = make_int2(0, 0);
     int varL = 0;
     float best = -3.0e38f, second = -3.0e38f;
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
       bad = varL == 0;
     }
     if (!bad) {
-      for (int im = lo + lane; im <= hi; im += 32) {
+      for (int im = lo + gl; im <= hi; im += G) {
         const long ft = (long)y * W + im;
         if (v.mask1[ft] != 255) continue;
         int2 sr = make_int2(0, 0);
@@ -323,17 +326,18 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
         if (key > best) { second = best; best = key; bi = im; }
         else if (key > second) second = key;
       }
-#pragma unroll
-      for (int o = 16; o; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o), os = __shfl_xor_sync(0xffffffffu, second, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
-        const float lo2 = fminf(best, ob);
-        if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
-        second = fmaxf(fmaxf(second, os), lo2);
-      }
     }
-    if (lane == 0) {
+    __syncwarp();
+#pragma unroll
+    for (int o = G / 2; o; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o, G), os = __shfl_xor_sync(0xffffffffu, second, o, G);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o, G);
+      nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o, G);
+      const float lo2 = fminf(best, ob);
+      if (ob > best || (ob == best && oi >= 0 && (bi < 0 || oi < bi))) { best = ob; bi = oi; }
+      second = fmaxf(fmaxf(second, os), lo2);
+    }
+    if (gl == 0 && have) {
       if (!bad && nvalid == 0) {
         // no masked candidate in range: the pixel keeps its value (NOMATCH)
       } else if (!bad && best >= 1.0e-6f * (float)varL && (nvalid == 1 || best - second > 1.0e-4f * best)) {
@@ -358,6 +362,7 @@ __global__ void __launch_bounds__(256) k_list_masked(const uint8_t* __restrict__
 }
 
 __global__ void k_count_add(const unsigned* __restrict__ n, unsigned long long* __restrict__ total) { *total += *n; }
+__global__ void k_count_add2(const unsigned* __restrict__ n2, unsigned long long* __restrict__ total2) { total2[0] += n2[0]; total2[1] += n2[1]; }
 
 template <int G, int MODE>
 static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, const short* lo_map, const short* hi_map,
@@ -372,7 +377,7 @@ static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, 
       dim3 gs((ms.width + 127) / 128, ms.height);
       k_ncc_screen5<MODE><<<gs, 128, 0, st>>>(v, ms, lo_map, hi_map, disp, sc->list, sc->n_list, sc->cap);
     }
-    k_ncc_screen_wide<MODE, false><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, lo, hi, disp, sc->list2, sc->n_list + 1);
+    k_ncc_screen_wide<MODE, false, (MODE == SEARCH_LOWEST ? 32 : 8)><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, lo, hi, disp, sc->list2, sc->n_list + 1);
     k_ncc_search_list<5, 32><<<148 * 4, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, lo, hi, disp);
     k_count_add<<<1, 1, 0, st>>>(sc->n_list + 1, sc->counters + 1);
     return 4;
@@ -483,9 +488,9 @@ int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, 
 // The two list kernels on a pixel list that is already filled (K3's band path, ncc_band.cu): any-width integer screening with the
 // window sums formed on the spot, then the exact pass for what is left (eight lanes per pixel: the ranges are narrow).
 int launch_range_lists(const PairViews& v, const short* lo_map, const short* hi_map, short* disp, const SearchScratch* sc, cudaStream_t st) {
-  k_ncc_screen_wide<SEARCH_RANGE_MAPS, true><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, 0, 0, disp, sc->list2,
+  k_ncc_screen_wide<SEARCH_RANGE_MAPS, true, 8><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, 0, 0, disp, sc->list2,
                                                                     sc->n_list + 1);
   k_ncc_search_list<5, 8><<<148 * 2, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, 0, 0, disp);
-  k_count_add<<<1, 1, 0, st>>>(sc->n_list + 1, sc->counters + 1);
+  k_count_add2<<<1, 1, 0, st>>>(sc->n_list, sc->counters);
   return 3;
 }

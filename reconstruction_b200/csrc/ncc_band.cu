@@ -37,16 +37,20 @@ constexpr int M1W = 192;
 constexpr int LPL = 80;     // words per parity plane of an expanded source row (67 used; 16 mod 32: the planes fall on disjoint banks)
 constexpr int RPL = 112;    // ... of an expanded target row (96 used)
 
+// shared-memory layout (bytes).  The window-sum table of the target strip (SR) overlays the raw staging buffers, which are
+// dead once the pixels have been expanded: 69 KB per CTA, three CTAs per SM.
 constexpr int OFF_RAWL = 0;
 constexpr int OFF_RAWR = 8064;                       // ROWS*400 = 8000, padded (the last 4-pixel group reads 8 bytes past a row)
-constexpr int OFF_M0 = OFF_RAWR + ROWS * RBOXW * 4;  // 19584
-constexpr int OFF_M1 = OFF_M0 + TR * M0W;            // 21888
-constexpr int OFF_LX = OFF_M1 + TR * M1W;            // 24960
-constexpr int OFF_RX = OFF_LX + ROWS * 2 * LPL * 4;  // 37760
-constexpr int OFF_SR = OFF_RX + ROWS * 2 * RPL * 4;  // 55680
-constexpr int OFF_SL = OFF_SR + TR * RPX * 8;        // 80256
-constexpr int OFF_MISC = OFF_SL + TR * TW * 8;       // 96640
+constexpr int OFF_SR = 0;                            // TR*RPX*8 = 24576 >= OFF_RAWR + ROWS*RBOXW*4 = 19584
+constexpr int OFF_M0 = 24576;
+constexpr int OFF_M1 = OFF_M0 + TR * M0W;            // 26880
+constexpr int OFF_LX = OFF_M1 + TR * M1W;            // 29952
+constexpr int OFF_RX = OFF_LX + ROWS * 2 * LPL * 4;  // 42752
+constexpr int OFF_SL = OFF_RX + ROWS * 2 * RPL * 4;  // 60672
+constexpr int OFF_MISC = OFF_SL + TR * TW * 4;       // 68864
 constexpr int SMEM_BYTES = OFF_MISC + 128;
+static_assert(OFF_RAWR + ROWS * RBOXW * 4 <= OFF_M0 && TR * RPX * 8 <= OFF_M0, "raw buffers / SR overlay");
+constexpr int FAKE_SUM = 110000;  // window sum stored for a target column that is not a candidate: its numerator is always negative
 
 struct BandMaps {
   CUtensorMap img0, img1;    // u32 views of the BGR rows, boxes LBOXW x ROWS / RBOXW x ROWS
@@ -64,18 +68,21 @@ struct BandArgs {
   unsigned cap;
 };
 
-// 3-byte pixels -> B,G,R,0 words, even and odd columns in separate planes (pixel p -> plane p & 1, word p >> 1)
+// 3-byte pixels -> B,G,R,0 words, even and odd columns in separate planes (pixel p -> plane p & 1, word p >> 1).
+// A warp takes the rows warp, warp + 8, ...; its lanes stride the 4-pixel groups of the row.
 template <int RAW_WORDS, int GROUPS, int PL>
-__device__ __forceinline__ void expand_rows(const unsigned* __restrict__ raw, unsigned* __restrict__ X, int tid) {
-  for (int i = tid; i < ROWS * GROUPS; i += NT) {
-    const int r = i / GROUPS, g = i - r * GROUPS;
-    const unsigned* s = raw + r * RAW_WORDS + 3 * g;
-    const unsigned w0 = s[0], w1 = s[1], w2 = s[2];
-    const unsigned p0 = w0 & 0x00ffffffu, p1 = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
-    const unsigned p2 = __funnelshift_r(w1, w2, 16) & 0x00ffffffu, p3 = w2 >> 8;
-    unsigned* d = X + r * 2 * PL + 2 * g;
-    *reinterpret_cast<uint2*>(d) = make_uint2(p0, p2);
-    *reinterpret_cast<uint2*>(d + PL) = make_uint2(p1, p3);
+__device__ __forceinline__ void expand_rows(const unsigned* __restrict__ raw, unsigned* __restrict__ X, int warp, int lane) {
+  for (int r = warp; r < ROWS; r += NT / 32) {
+    const unsigned* s = raw + r * RAW_WORDS;
+    unsigned* d = X + r * 2 * PL;
+#pragma unroll
+    for (int g = lane; g < GROUPS; g += 32) {
+      const unsigned w0 = s[3 * g], w1 = s[3 * g + 1], w2 = s[3 * g + 2];
+      const unsigned p0 = w0 & 0x00ffffffu, p1 = __funnelshift_r(w0, w1, 24) & 0x00ffffffu;
+      const unsigned p2 = __funnelshift_r(w1, w2, 16) & 0x00ffffffu, p3 = w2 >> 8;
+      *reinterpret_cast<uint2*>(d + 2 * g) = make_uint2(p0, p2);
+      *reinterpret_cast<uint2*>(d + PL + 2 * g) = make_uint2(p1, p3);
+    }
   }
 }
 
@@ -105,7 +112,7 @@ __device__ __forceinline__ void column_window_sums(const unsigned* __restrict__ 
   }
 }
 
-__global__ void __launch_bounds__(NT, 2) k_ncc_band(const __grid_constant__ BandArgs a, const __grid_constant__ BandMaps tm) {
+__global__ void __launch_bounds__(NT, 3) k_ncc_band(const __grid_constant__ BandArgs a, const __grid_constant__ BandMaps tm) {
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned* rawL = reinterpret_cast<unsigned*>(smem + OFF_RAWL);
   unsigned* rawR = reinterpret_cast<unsigned*>(smem + OFF_RAWR);
@@ -113,8 +120,8 @@ __global__ void __launch_bounds__(NT, 2) k_ncc_band(const __grid_constant__ Band
   const uint8_t* m1 = smem + OFF_M1;
   unsigned* LX = reinterpret_cast<unsigned*>(smem + OFF_LX);
   unsigned* RX = reinterpret_cast<unsigned*>(smem + OFF_RX);
-  int2* SR = reinterpret_cast<int2*>(smem + OFF_SR);  // [TR][RPX] (sum, float bits of 1/var; NaN = not a candidate)
-  int2* SL = reinterpret_cast<int2*>(smem + OFF_SL);  // [TR][TW]  (sum, var)
+  int2* SR = reinterpret_cast<int2*>(smem + OFF_SR);  // [TR][RPX] (sum, float bits of 1/var); overlays the raw buffers
+  unsigned* SL = reinterpret_cast<unsigned*>(smem + OFF_SL);  // [TR][TW]  sum | ceil(var / 4096) << 15
   int* misc = reinterpret_cast<int*>(smem + OFF_MISC);  // [0..3] mbarriers (2 x 8 B), [4..11] warp minima, [12..19] warp maxima
   const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem);
   const unsigned barL = sbase + OFF_MISC, barR = barL + 8;
@@ -177,25 +184,32 @@ __global__ void __launch_bounds__(NT, 2) k_ncc_band(const __grid_constant__ Band
     tma_load_2d(sbase + OFF_M1, &tm.mask1, xr, ys, barR);
   }
   mbar_wait(barL, 0);
-  expand_rows<LBOXW, 34, LPL>(rawL, LX, tid);
+  expand_rows<LBOXW, 34, LPL>(rawL, LX, warp, lane);
   mbar_wait(barR, 0);
-  expand_rows<RBOXW, 48, RPL>(rawR, RX, tid);
+  expand_rows<RBOXW, 48, RPL>(rawR, RX, warp, lane);
   __syncthreads();
 
   // ---- window sums: target columns 2..189 of the box, source columns 3..130 ----
+  // (SR overlays the raw buffers: every warp is past its expansion reads here)
   for (int task = tid; task < 188 + TW; task += NT) {
     if (task < 188) {
       const int c = task + 2;
       const bool col_ok = xr + c >= XL1 && xr + c <= XR1;
       column_window_sums<RPL>(RX, c, [&](int row, int s1, int s2) {
         const int var = 75 * s2 - s1 * s1;
-        float rv = var ? 1.0f / (float)var : 0.0f;
-        if (!col_ok || m1[row * M1W + c] != 255) rv = __int_as_float(0x7fc00000);
-        SR[row * RPX + c] = make_int2(s1, __float_as_int(rv));
+        float rv;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rv) : "f"((float)var));
+        if (var == 0) rv = 0.0f;
+        const bool cand = col_ok && m1[row * M1W + c] == 255;
+        // not a candidate: a sum that makes the numerator negative whatever the source window is (75 SumLR <= 19125 SumL)
+        SR[row * RPX + c] = cand ? make_int2(s1, __float_as_int(rv)) : make_int2(FAKE_SUM, __float_as_int(1.0e-12f));
       });
     } else {
       const int c = task - 188 + 3;
-      column_window_sums<LPL>(LX, c, [&](int row, int s1, int s2) { SL[row * TW + c - 3] = make_int2(s1, 75 * s2 - s1 * s1); });
+      column_window_sums<LPL>(LX, c, [&](int row, int s1, int s2) {
+        const unsigned var = (unsigned)(75 * s2 - s1 * s1);
+        SL[row * TW + c - 3] = (unsigned)s1 | (((var + 4095u) >> 12) << 15);
+      });
     }
   }
   __syncthreads();
@@ -254,26 +268,27 @@ __global__ void __launch_bounds__(NT, 2) k_ncc_band(const __grid_constant__ Band
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         const int row = 2 * warp + (p >> 1), dx = p & 1;
-        const int2 sl = SL[row * TW + 2 * q + dx];
+        const unsigned slp = SL[row * TW + 2 * q + dx];
+        const int sumL = (int)(slp & 0x7fffu);
+        const float varL = (float)(slp >> 15) * 4096.0f;  // rounded up to a multiple of 4096: the correlation floor below is not sharp
         const int2* sr = SR + row * RPX + rc0 + 2 + dx;
         float best = -3.0e38f, second = -3.0e38f;
 #pragma unroll
         for (int e = 0; e < 5; e++) {
           const int S = (p == 0 ? P00[e] + A0[e] : p == 1 ? P10[e] + A5[e] : p == 2 ? P01[e] + A0[e] : P11[e] + A5[e]) + MM[e];
           const int2 st = sr[e];
-          const int num = 75 * S - sl.x * st.x;
+          const int num = 75 * S - sumL * st.x;
           const float fn = (float)num;
-          float key = fmaxf(fn * fabsf(fn) * __int_as_float(st.y), -3.0e38f);  // NaN (not a candidate) -> -3e38
+          float key = fn * fabsf(fn) * __int_as_float(st.y);
           key = __int_as_float((__float_as_int(key) & ~7) | e);
           second = fmaxf(second, fminf(best, key));
           best = fmaxf(best, key);
         }
         if (act & (1u << p)) {
-          if (best > -2.0e38f) {  // at least one candidate
-            const bool settled = sl.y != 0 && best >= 1.0e-6f * (float)sl.y && best - second > 3.0e-5f * best;
-            if (settled) bestj[p] = (__float_as_int(best) & 7) + 1;
-            else tolist |= 1u << p;
-          }
+          // best <= 0 also covers "no candidate at all" (every key then comes from a FAKE_SUM entry): the list kernels sort it out
+          const bool settled = best >= 1.0e-6f * varL && varL != 0.0f && best - second > 3.0e-5f * best;
+          if (settled) bestj[p] = (__float_as_int(best) & 7) + 1;
+          else tolist |= 1u << p;
         }
       }
     } else if (act) {
@@ -313,7 +328,7 @@ __global__ void __launch_bounds__(NT, 2) k_ncc_band(const __grid_constant__ Band
 // Only the hole pixels need the result (the others are ranged by k_ncc_band itself): those with a non-empty range get it
 // written to the range maps and are appended to the pixel list.
 // ------------------------------------------------------------------------------------------------
-constexpr int HU = 4;
+constexpr int HU = 8;  // chunks whose loads are in flight together (the walk is a chain of dependent iterations: latency-bound)
 __global__ void __launch_bounds__(128) k_hole_ranges(const uint8_t* __restrict__ mask0, int W, Bound ms, Bound mt, int off,
                                                      const double* __restrict__ prev, int pw, short* __restrict__ lo_map,
                                                      short* __restrict__ hi_map, unsigned* __restrict__ list,
@@ -431,10 +446,18 @@ int launch_high_match_band(const PairViews& v, Bound ms, Bound mt, int offset, c
   if (ms.width <= 0 || ms.height <= 0) return n;
   cudaMemsetAsync(sc->n_list, 0, 2 * sizeof(unsigned), st);
   {
+    // holes on the side stream, concurrently with the band kernel (both append to the same list; the range maps they write
+    // are disjoint): the walk along a scanline is latency-bound and takes few SM resources
+    cudaStream_t hs = sc->side ? sc->side : st;
+    if (sc->side) {
+      cudaEventRecord(sc->ev_fork, st);
+      cudaStreamWaitEvent(sc->side, sc->ev_fork, 0);
+    }
     int warps = 4;
     while (warps > 1 && (size_t)warps * pw * sizeof(int) > 48 * 1024) warps >>= 1;
-    k_hole_ranges<<<(ms.height + warps - 1) / warps, warps * 32, warps * pw * sizeof(int), st>>>(v.mask0, v.W, ms, mt, offset, prev, pw, lo_map,
+    k_hole_ranges<<<(ms.height + warps - 1) / warps, warps * 32, warps * pw * sizeof(int), hs>>>(v.mask0, v.W, ms, mt, offset, prev, pw, lo_map,
                                                                                              hi_map, sc->list, sc->n_list, sc->cap);
+    if (sc->side) cudaEventRecord(sc->ev_join, sc->side);
     n++;
   }
   {
@@ -456,5 +479,6 @@ int launch_high_match_band(const PairViews& v, Bound ms, Bound mt, int offset, c
     k_ncc_band<<<dim3(gx, gy), NT, SMEM_BYTES, st>>>(a, tm);
     n++;
   }
+  if (sc->side) cudaStreamWaitEvent(st, sc->ev_join, 0);
   return n;
 }

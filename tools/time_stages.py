@@ -24,7 +24,8 @@ print("  per level (ms): stage " + " ".join(f"L{lv:<6d}" for lv in range(L)))
 for st in list(range(2, 11)) + [12]:
     print(f"  {st:2d} {(capi.STAGE_NAMES.get(st) or 'RefineSweeps'):22s} " + " ".join(f"{lvl[st][lv]:7.3f}" for lv in range(L)))
 print("     level totals           " + " ".join(f"{sum(lvl[st][lv] for st in range(2, 11)):7.3f}" for lv in range(L)))
-print("  total stages %.3f ms; refine out-of-table evals %d" % (ms[:12].sum(), g.refine_counters()[1]))
+sc = g.search_counters(reset=False)
+print("  total stages %.3f ms; refine out-of-table evals %d; NCC search: %d px listed by the band kernel, %d px to the exact pass (all reps)" % (ms[:12].sum(), g.refine_counters()[1], sc[0], sc[1]))
 if sl:
     print("  refine sweeps: %.3f ms over %d sweeps (%.1f us/sweep), %.3f G px-iter, %.1f GB/s algorithmic (22 B/px-iter)" % (sm, sl, 1e3 * sm / sl, spx / 1e9, 22 * spx / (sm * 1e-3) / 1e9))
 W, H = sp.top_size
