@@ -31,15 +31,17 @@ struct sb200_ctx {
   int device = 0, L = 0, W0 = 0, H0 = 0, OW = 0, OH = 0, R = 2, offset = 2, refine_override = -1;
   double ws = 0.5;
   cudaStream_t st = nullptr;
-  cudaStream_t side = nullptr;  // forked from st for kernels that run beside the main one of a stage (hole ranges of K3)
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // K3 (HighLevelInitialMatch): direction 1 runs on `side` beside direction 0 on `st`, each direction's hole ranges on its own
+  // stream beside its band kernel; fork / join through events (capturable into a CUDA graph)
+  cudaStream_t side = nullptr, hole_s[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hf[2] = {nullptr, nullptr}, ev_hj[2] = {nullptr, nullptr};
   std::vector<Level> lv;
   int* d_margins = nullptr;  // [L][2][4]
   bool uploaded = false, calib_set = false;
   // disparity state (cv::Mat disparity[2] of MatchAllLayer)
   short* ds[2] = {nullptr, nullptr};
   short* ds_tmp = nullptr;
-  short *range_lo = nullptr, *range_hi = nullptr;
+  short *range_lo[2] = {nullptr, nullptr}, *range_hi[2] = {nullptr, nullptr};  // per direction (the two directions of K3 run concurrently)
   short *BL[2] = {nullptr, nullptr}, *BR[2] = {nullptr, nullptr};
   double* f64buf[4] = {nullptr, nullptr, nullptr, nullptr};
   double* dd[2] = {nullptr, nullptr};
@@ -48,10 +50,11 @@ struct sb200_ctx {
   double2* stats[2] = {nullptr, nullptr};
   int2* istats[2] = {nullptr, nullptr};
   unsigned long long* search_counters = nullptr;  // [2]: [1] = pixels the screening pass left to the exact search
-  unsigned* search_list = nullptr;
-  unsigned* search_list2 = nullptr;
-  unsigned* search_n = nullptr;
-  SearchScratch ss{};
+  unsigned* search_list[2] = {nullptr, nullptr};
+  unsigned* search_list2[2] = {nullptr, nullptr};
+  unsigned* search_listw[2] = {nullptr, nullptr};
+  unsigned* search_n = nullptr;  // [2][4]
+  SearchScratch ss{}, ss1{};     // per direction; everything sequential uses ss
   bool screen = true;                             // SB200_SCREEN=0 disables the integer screening pass
   bool band = true;                               // SB200_BAND=0: K3 through the register-resident screening kernel instead of ncc_band.cu
   int stats_level = -1;
@@ -193,11 +196,20 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           c->err = "HighLevelInitialMatch needs the refined f64 maps of the previous level";
           return SB200_ERR_STATE;
         }
+        if (band) {  // direction 1 on the side stream
+          CK(cudaEventRecord(c->ev_fork, c->st));
+          CK(cudaStreamWaitEvent(c->side, c->ev_fork, 0));
+        }
         for (int d = 0; d < 2; d++) {
+          cudaStream_t sd = (band && d == 1) ? c->side : c->st;
           const int n = launch_high_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->offset, c->dd[d], c->dw,
-                                          c->dh, c->range_lo, c->range_hi, c->ds[d], (c->screen && c->R == 2) ? &c->ss : nullptr, band, c->st);
+                                          c->dh, c->range_lo[d], c->range_hi[d], c->ds[d], (c->screen && c->R == 2) ? (d ? &c->ss1 : &c->ss) : nullptr, band, sd);
           if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
           c->launches += n;
+        }
+        if (band) {
+          CK(cudaEventRecord(c->ev_join, c->side));
+          CK(cudaStreamWaitEvent(c->st, c->ev_join, 0));
         }
       }
       c->dw = W; c->dh = H; c->elem = 2;
@@ -386,20 +398,28 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
     CK(dalloc(&c->istats[d], n + pad));
   }
   CK(dalloc(&c->search_counters, 2));
-  CK(dalloc(&c->search_list, n + pad));
-  CK(dalloc(&c->search_list2, n + pad));
-  CK(dalloc(&c->search_n, 2));
-  c->ss.list = c->search_list; c->ss.list2 = c->search_list2; c->ss.n_list = c->search_n; c->ss.cap = (unsigned)n; c->ss.counters = c->search_counters;
+  CK(dalloc(&c->search_n, 8));
   CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
-  c->ss.side = c->side; c->ss.ev_fork = c->ev_fork; c->ss.ev_join = c->ev_join;
+  for (int d = 0; d < 2; d++) {
+    CK(dalloc(&c->search_list[d], n + pad));
+    CK(dalloc(&c->search_list2[d], n + pad));
+    CK(dalloc(&c->search_listw[d], n + pad));
+    CK(dalloc(&c->range_lo[d], n + pad));
+    CK(dalloc(&c->range_hi[d], n + pad));
+    CK(cudaStreamCreateWithFlags(&c->hole_s[d], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_hf[d], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_hj[d], cudaEventDisableTiming));
+    SearchScratch& q = d ? c->ss1 : c->ss;
+    q.list = c->search_list[d]; q.list2 = c->search_list2[d]; q.list_wide = c->search_listw[d]; q.n_list = c->search_n + 4 * d;
+    q.cap = (unsigned)n; q.counters = c->search_counters;
+    q.side = c->hole_s[d]; q.ev_fork = c->ev_hf[d]; q.ev_join = c->ev_hj[d];
+  }
   CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
   if (const char* e = getenv("SB200_BAND")) c->band = atoi(e) != 0;
   CK(dalloc(&c->ds_tmp, n + pad));
-  CK(dalloc(&c->range_lo, n + pad));
-  CK(dalloc(&c->range_hi, n + pad));
   for (int k = 0; k < 4; k++) CK(dalloc(&c->f64buf[k], n + pad));
   for (int d = 0; d < 2; d++) {
     CK(dalloc(&c->rs[d].table, (size_t)SB_REFINE_K * n + pad));
@@ -447,7 +467,13 @@ void sb200_ctx_destroy(sb200_ctx* c) {
     for (int k = 0; k < 2; k++) { cudaFree(l.img[k]); cudaFree(l.mask[k]); }
   cudaFree(c->d_margins);
   for (int d = 0; d < 2; d++) { cudaFree(c->ds[d]); cudaFree(c->BL[d]); cudaFree(c->BR[d]); cudaFree(c->stats[d]); cudaFree(c->istats[d]); }
-  cudaFree(c->ds_tmp); cudaFree(c->range_lo); cudaFree(c->range_hi); cudaFree(c->search_counters); cudaFree(c->search_list); cudaFree(c->search_list2); cudaFree(c->search_n);
+  cudaFree(c->ds_tmp); cudaFree(c->search_counters); cudaFree(c->search_n);
+  for (int d = 0; d < 2; d++) {
+    cudaFree(c->range_lo[d]); cudaFree(c->range_hi[d]); cudaFree(c->search_list[d]); cudaFree(c->search_list2[d]); cudaFree(c->search_listw[d]);
+    if (c->hole_s[d]) { cudaStreamSynchronize(c->hole_s[d]); cudaStreamDestroy(c->hole_s[d]); }
+    if (c->ev_hf[d]) cudaEventDestroy(c->ev_hf[d]);
+    if (c->ev_hj[d]) cudaEventDestroy(c->ev_hj[d]);
+  }
   for (int k = 0; k < 4; k++) cudaFree(c->f64buf[k]);
   for (int d = 0; d < 2; d++) { cudaFree(c->rs[d].table); cudaFree(c->rs[d].code); cudaFree(c->rs[d].miss_count); cudaFree(c->rs[d].miss_list); }
   cudaFree(c->rs[0].counters);

@@ -23,7 +23,8 @@ int launch_window_stats(const uint8_t* img, int W, int H, int R, double2* stats,
 struct SearchScratch {
   unsigned* list;                // flat pixel indices left by the per-thread screening pass (or all masked pixels, lowest level)
   unsigned* list2;               // ... left by the per-warp screening pass: input of the exact pass
-  unsigned* n_list;              // device counters [2] of the current search
+  unsigned* list_wide;           // K3 band path: listed pixels whose candidate range is wide (a whole warp screens each)
+  unsigned* n_list;              // device counters [4] of the current search: [0] list, [1] list2, [2] list_wide
   unsigned cap;
   unsigned long long* counters;  // [2]: [0] += pixels listed, [1] += pixels left to the exact pass, after every search (instrumentation)
   cudaStream_t side;             // optional second stream (+ fork / join events) for work that runs beside the main kernel

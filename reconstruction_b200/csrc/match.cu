@@ -299,22 +299,26 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
     if (!bad) {
       for (int im = lo + gl; im <= hi; im += G) {
         const long ft = (long)y * W + im;
-        if (v.mask1[ft] != 255) continue;
+        // the mask byte and the window rows are requested together (lo >= 2, hi <= W-3: the window is inside the image),
+        // one memory round trip per candidate
+        const unsigned char mk = v.mask1[ft];
         int2 sr = make_int2(0, 0);
         if (!ONFLY) sr = v.istat1[ft];
+        unsigned q[5][4];
+#pragma unroll
+        for (int r = 0; r < 5; r++) load_row_words<4>(v.img1, ((long)(y - 2 + r) * W + (im - 2)) * 3, q[r]);
+        if (mk != 255) continue;
         unsigned slr = 0;
 #pragma unroll
         for (int r = 0; r < 5; r++) {
-          unsigned q[4];
-          load_row_words<4>(v.img1, ((long)(y - 2 + r) * W + (im - 2)) * 3, q);
 #pragma unroll
-          for (int i = 0; i < 4; i++) slr = __dp4a(L[r][i], q[i], slr);
+          for (int i = 0; i < 4; i++) slr = __dp4a(L[r][i], q[r][i], slr);
           if (ONFLY) {
-            q[3] &= 0x00ffffffu;
+            q[r][3] &= 0x00ffffffu;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-              sr.x = (int)__dp4a(q[i], 0x01010101u, (unsigned)sr.x);
-              sr.y = (int)__dp4a(q[i], q[i], (unsigned)sr.y);
+              sr.x = (int)__dp4a(q[r][i], 0x01010101u, (unsigned)sr.x);
+              sr.y = (int)__dp4a(q[r][i], q[r][i], (unsigned)sr.y);
             }
           }
         }
@@ -361,8 +365,12 @@ __global__ void __launch_bounds__(256) k_list_masked(const uint8_t* __restrict__
   if (e < cap) list[e] = (unsigned)f;
 }
 
-__global__ void k_count_add(const unsigned* __restrict__ n, unsigned long long* __restrict__ total) { *total += *n; }
-__global__ void k_count_add2(const unsigned* __restrict__ n2, unsigned long long* __restrict__ total2) { total2[0] += n2[0]; total2[1] += n2[1]; }
+// (atomics: the two matching directions of a level may run on two streams and share the totals)
+__global__ void k_count_add(const unsigned* __restrict__ n, unsigned long long* __restrict__ total) { atomicAdd(total, (unsigned long long)*n); }
+__global__ void k_count_add2(const unsigned* __restrict__ n3, unsigned long long* __restrict__ total2) {
+  atomicAdd(total2, (unsigned long long)n3[0] + n3[2]);
+  atomicAdd(total2 + 1, (unsigned long long)n3[1]);
+}
 
 template <int G, int MODE>
 static int search_dispatch(const PairViews& v, Bound ms, int R, int lo, int hi, const short* lo_map, const short* hi_map,
@@ -489,8 +497,10 @@ int launch_rematch_search(const PairViews& v, Bound ms, int R, const short* BL, 
 // window sums formed on the spot, then the exact pass for what is left (eight lanes per pixel: the ranges are narrow).
 int launch_range_lists(const PairViews& v, const short* lo_map, const short* hi_map, short* disp, const SearchScratch* sc, cudaStream_t st) {
   k_ncc_screen_wide<SEARCH_RANGE_MAPS, true, 8><<<148 * 8, 256, 0, st>>>(v, sc->list, sc->n_list, sc->cap, lo_map, hi_map, 0, 0, disp, sc->list2,
-                                                                    sc->n_list + 1);
+                                                                       sc->n_list + 1);
+  k_ncc_screen_wide<SEARCH_RANGE_MAPS, true, 32><<<148 * 8, 256, 0, st>>>(v, sc->list_wide, sc->n_list + 2, sc->cap, lo_map, hi_map, 0, 0, disp,
+                                                                        sc->list2, sc->n_list + 1);
   k_ncc_search_list<5, 8><<<148 * 2, 256, 0, st>>>(v, sc->list2, sc->n_list + 1, sc->cap, lo_map, hi_map, 0, 0, disp);
   k_count_add2<<<1, 1, 0, st>>>(sc->n_list, sc->counters);
-  return 3;
+  return 4;
 }

@@ -34,8 +34,9 @@ constexpr int RPX = 192;    // staged target columns
 constexpr int RBOXW = 144;  // 576 B
 constexpr int M0W = 144;    // mask bytes per staged row
 constexpr int M1W = 192;
-constexpr int LPL = 80;     // words per parity plane of an expanded source row (67 used; 16 mod 32: the planes fall on disjoint banks)
-constexpr int RPL = 112;    // ... of an expanded target row (96 used)
+constexpr int LPL = 80;     // words per parity plane of an expanded source row (67 used)
+constexpr int RPL = 96;     // ... of an expanded target row.  A multiple of 32: when the coarse disparity steps by one inside a warp,
+                            // the lanes on either side of the step read different planes at (nearly) the same word offset
 
 // shared-memory layout (bytes).  The window-sum table of the target strip (SR) overlays the raw staging buffers, which are
 // dead once the pixels have been expanded: 69 KB per CTA, three CTAs per SM.
@@ -46,8 +47,8 @@ constexpr int OFF_M0 = 24576;
 constexpr int OFF_M1 = OFF_M0 + TR * M0W;            // 26880
 constexpr int OFF_LX = OFF_M1 + TR * M1W;            // 29952
 constexpr int OFF_RX = OFF_LX + ROWS * 2 * LPL * 4;  // 42752
-constexpr int OFF_SL = OFF_RX + ROWS * 2 * RPL * 4;  // 60672
-constexpr int OFF_MISC = OFF_SL + TR * TW * 4;       // 68864
+constexpr int OFF_SL = OFF_RX + ROWS * 2 * RPL * 4;  // 58112
+constexpr int OFF_MISC = OFF_SL + TR * TW * 4;       // 66304
 constexpr int SMEM_BYTES = OFF_MISC + 128;
 static_assert(OFF_RAWR + ROWS * RBOXW * 4 <= OFF_M0 && TR * RPX * 8 <= OFF_M0, "raw buffers / SR overlay");
 constexpr int FAKE_SUM = 110000;  // window sum stored for a target column that is not a candidate: its numerator is always negative
@@ -86,9 +87,9 @@ __device__ __forceinline__ void expand_rows(const unsigned* __restrict__ raw, un
   }
 }
 
-// Exact sums over the 5x5 window centred on column c of every tile row 2..17 (image rows ys .. ys+15): a thread walks
-// down its column with the row sums of the last five rows in registers.  emit(row 0..15, sum, sum of squares).
-template <int PL, class Emit>
+// Exact sums over the 5x5 window centred on column c for the tile rows R0+2 .. R0+NR-3: a thread walks down its column with
+// the row sums of the last five rows in registers.  emit(window row index - 2 = image row - ys, sum, sum of squares).
+template <int PL, int R0, int NR, class Emit>
 __device__ __forceinline__ void column_window_sums(const unsigned* __restrict__ X, int c, Emit emit) {
   int a[5];
 #pragma unroll
@@ -96,8 +97,8 @@ __device__ __forceinline__ void column_window_sums(const unsigned* __restrict__ 
   int h1[5], h2[5];
   int v1 = 0, v2 = 0;
 #pragma unroll
-  for (int r = 0; r < ROWS; r++) {
-    const unsigned* row = X + r * 2 * PL;
+  for (int i = 0; i < NR; i++) {
+    const unsigned* row = X + (R0 + i) * 2 * PL;
     int s1 = 0, s2 = 0;
 #pragma unroll
     for (int k = 0; k < 5; k++) {
@@ -105,10 +106,10 @@ __device__ __forceinline__ void column_window_sums(const unsigned* __restrict__ 
       s1 = (int)__dp4a(px, 0x00010101u, (unsigned)s1);
       s2 = (int)__dp4a(px, px, (unsigned)s2);
     }
-    if (r >= 5) { v1 -= h1[r % 5]; v2 -= h2[r % 5]; }
-    h1[r % 5] = s1; h2[r % 5] = s2;
+    if (i >= 5) { v1 -= h1[i % 5]; v2 -= h2[i % 5]; }
+    h1[i % 5] = s1; h2[i % 5] = s2;
     v1 += s1; v2 += s2;
-    if (r >= 4) emit(r - 4, v1, v2);
+    if (i >= 4) emit(R0 + i - 4, v1, v2);
   }
 }
 
@@ -189,29 +190,36 @@ __global__ void __launch_bounds__(NT, 3) k_ncc_band(const __grid_constant__ Band
   expand_rows<RBOXW, 48, RPL>(rawR, RX, warp, lane);
   __syncthreads();
 
-  // ---- window sums: target columns 2..189 of the box, source columns 3..130 ----
-  // (SR overlays the raw buffers: every warp is past its expansion reads here)
-  for (int task = tid; task < 188 + TW; task += NT) {
-    if (task < 188) {
-      const int c = task + 2;
-      const bool col_ok = xr + c >= XL1 && xr + c <= XR1;
-      column_window_sums<RPL>(RX, c, [&](int row, int s1, int s2) {
-        const int var = 75 * s2 - s1 * s1;
-        float rv;
-        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rv) : "f"((float)var));
-        if (var == 0) rv = 0.0f;
-        const bool cand = col_ok && m1[row * M1W + c] == 255;
-        // not a candidate: a sum that makes the numerator negative whatever the source window is (75 SumLR <= 19125 SumL)
-        SR[row * RPX + c] = cand ? make_int2(s1, __float_as_int(rv)) : make_int2(FAKE_SUM, __float_as_int(1.0e-12f));
-      });
-    } else {
-      const int c = task - 188 + 3;
-      column_window_sums<LPL>(LX, c, [&](int row, int s1, int s2) {
-        const unsigned var = (unsigned)(75 * s2 - s1 * s1);
-        SL[row * TW + c - 3] = (unsigned)s1 | (((var + 4095u) >> 12) << 15);
-      });
-    }
-  }
+  // ---- window sums: target columns 2..189 of the box (whole columns), source columns 3..130 (two half columns each) ----
+  // (SR overlays the raw buffers: every warp is past its expansion reads here.)  Lanes take columns of one parity, so every
+  // tap of a warp reads one plane at consecutive words.  188 + 256 tasks: the first 188 threads walk 20 rows of a target
+  // column while the others take a 12-row half of a source column; the remaining halves follow on all threads.
+  auto emitR = [&](int c) {
+    const bool col_ok = xr + c >= XL1 && xr + c <= XR1;
+    int2* dst = SR + ((c & 1) ? RPX / 2 : 0) + (c >> 1);
+    column_window_sums<RPL, 0, ROWS>(RX, c, [&](int row, int s1, int s2) {
+      const int var = 75 * s2 - s1 * s1;
+      float rv;
+      asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rv) : "f"((float)var));
+      if (var == 0) rv = 0.0f;
+      const bool cand = col_ok && m1[row * M1W + c] == 255;
+      // not a candidate: a sum that makes the numerator negative whatever the source window is (75 SumLR <= 19125 SumL)
+      dst[row * RPX] = cand ? make_int2(s1, __float_as_int(rv)) : make_int2(FAKE_SUM, __float_as_int(1.0e-12f));
+    });
+  };
+  auto emitL = [&](int h) {  // h in [0, 256): column parity-major, then half
+    const int half = h >> 7, t = h & 127;
+    const int c = 3 + ((t < 64) ? 2 * t + 1 : 2 * (t - 64));  // 4, 6, .., 130 | 3, 5, .., 129
+    auto put = [&](int row, int s1, int s2) {
+      const unsigned var = (unsigned)(75 * s2 - s1 * s1);
+      SL[row * TW + c - 3] = (unsigned)s1 | (((var + 4095u) >> 12) << 15);
+    };
+    if (half == 0) column_window_sums<LPL, 0, 12>(LX, c, put);
+    else column_window_sums<LPL, 8, 12>(LX, c, put);
+  };
+  if (tid < 188) emitR(tid < 94 ? 2 + 2 * tid : 3 + 2 * (tid - 94));
+  else emitL(tid - 188);
+  if (tid + 68 < 256) emitL(tid + 68);
   __syncthreads();
 
   // ---- the quads ----
@@ -265,18 +273,26 @@ __global__ void __launch_bounds__(NT, 3) k_ncc_band(const __grid_constant__ Band
         }
       }
       // ---- keys: exact integer numerators, float ratio with the candidate index in the three low mantissa bits ----
+      int2 E[2][6];  // window sums of the six target columns rc0+2 .. rc0+7 on the quad's two rows (planes by column parity)
+      {
+        const int i0 = rc0 + 2;
+        const int s0 = ((i0 & 1) ? RPX / 2 : 0) + (i0 >> 1), s1 = (((i0 + 1) & 1) ? RPX / 2 : 0) + ((i0 + 1) >> 1);
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+          for (int m = 0; m < 6; m++) E[dy][m] = SR[(2 * warp + dy) * RPX + ((m & 1) ? s1 + (m - 1) / 2 : s0 + m / 2)];
+      }
 #pragma unroll
       for (int p = 0; p < 4; p++) {
         const int row = 2 * warp + (p >> 1), dx = p & 1;
         const unsigned slp = SL[row * TW + 2 * q + dx];
         const int sumL = (int)(slp & 0x7fffu);
         const float varL = (float)(slp >> 15) * 4096.0f;  // rounded up to a multiple of 4096: the correlation floor below is not sharp
-        const int2* sr = SR + row * RPX + rc0 + 2 + dx;
         float best = -3.0e38f, second = -3.0e38f;
 #pragma unroll
         for (int e = 0; e < 5; e++) {
           const int S = (p == 0 ? P00[e] + A0[e] : p == 1 ? P10[e] + A5[e] : p == 2 ? P01[e] + A0[e] : P11[e] + A5[e]) + MM[e];
-          const int2 st = sr[e];
+          const int2 st = E[p >> 1][dx + e];
           const int num = 75 * S - sumL * st.x;
           const float fn = (float)num;
           float key = fn * fabsf(fn) * __int_as_float(st.y);
@@ -332,7 +348,7 @@ constexpr int HU = 8;  // chunks whose loads are in flight together (the walk is
 __global__ void __launch_bounds__(128) k_hole_ranges(const uint8_t* __restrict__ mask0, int W, Bound ms, Bound mt, int off,
                                                      const double* __restrict__ prev, int pw, short* __restrict__ lo_map,
                                                      short* __restrict__ hi_map, unsigned* __restrict__ list,
-                                                     unsigned* __restrict__ n_list, unsigned cap) {
+                                                     unsigned* __restrict__ list_wide, unsigned* __restrict__ n_list, unsigned cap) {
   extern __shared__ int s_next[];  // [warps][pw]: (int(2 s[i']) << 14) | i'  for the first valid coarse index i' > i, low bits 0x3fff = none
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int y = ms.YL + blockIdx.x * (blockDim.x >> 5) + warp;
@@ -407,17 +423,23 @@ __global__ void __launch_bounds__(128) k_hole_ranges(const uint8_t* __restrict__
       const int fromL = __shfl_sync(0xffffffffu, valL, srcL), fromR = __shfl_sync(0xffffffffu, valR, srcR);
       const int bL = hasL ? valL : (mL ? fromL : carryL);
       const int bR = hasR ? valR : (mR ? fromR : carryR);
-      const bool put = hole && bR >= bL;
+      // narrow ranges go to the list eight lanes screen, wide ones (carried bounds far apart) to the list a whole warp screens
+      const bool put = hole && bR >= bL, wide = put && bR - bL >= 16;
       const unsigned balP = __ballot_sync(0xffffffffu, put);
       if (balP) {
-        unsigned e0 = 0;
-        if (lane == (__ffs(balP) - 1)) e0 = atomicAdd(n_list, (unsigned)__popc(balP));
-        e0 = __shfl_sync(0xffffffffu, e0, __ffs(balP) - 1);
+        const unsigned balW = __ballot_sync(0xffffffffu, wide), balN = balP & ~balW;
+        unsigned eN = 0, eW = 0;
+        if (lane == 0) {
+          if (balN) eN = atomicAdd(n_list, (unsigned)__popc(balN));
+          if (balW) eW = atomicAdd(n_list + 2, (unsigned)__popc(balW));
+        }
+        eN = __shfl_sync(0xffffffffu, eN, 0);
+        eW = __shfl_sync(0xffffffffu, eW, 0);
         if (put) {
-          const unsigned e = e0 + __popc(balP & lower);
+          const unsigned e = wide ? eW + __popc(balW & lower) : eN + __popc(balN & lower);
           if (e < cap) {
             const size_t f = (size_t)y * W + x;
-            list[e] = (unsigned)f;
+            (wide ? list_wide : list)[e] = (unsigned)f;
             lo_map[f] = (short)bL;
             hi_map[f] = (short)bR;
           }
@@ -444,7 +466,7 @@ int launch_high_match_band(const PairViews& v, Bound ms, Bound mt, int offset, c
     return -2;
   int n = launch_fill_s16(out, (long)v.W * v.H, (short)SB_NOMATCH, st);
   if (ms.width <= 0 || ms.height <= 0) return n;
-  cudaMemsetAsync(sc->n_list, 0, 2 * sizeof(unsigned), st);
+  cudaMemsetAsync(sc->n_list, 0, 4 * sizeof(unsigned), st);
   {
     // holes on the side stream, concurrently with the band kernel (both append to the same list; the range maps they write
     // are disjoint): the walk along a scanline is latency-bound and takes few SM resources
@@ -456,7 +478,7 @@ int launch_high_match_band(const PairViews& v, Bound ms, Bound mt, int offset, c
     int warps = 4;
     while (warps > 1 && (size_t)warps * pw * sizeof(int) > 48 * 1024) warps >>= 1;
     k_hole_ranges<<<(ms.height + warps - 1) / warps, warps * 32, warps * pw * sizeof(int), hs>>>(v.mask0, v.W, ms, mt, offset, prev, pw, lo_map,
-                                                                                             hi_map, sc->list, sc->n_list, sc->cap);
+                                                                                             hi_map, sc->list, sc->list_wide, sc->n_list, sc->cap);
     if (sc->side) cudaEventRecord(sc->ev_join, sc->side);
     n++;
   }
