@@ -117,7 +117,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
-def cpu_run(kind, L, w0, h0, steps, warmup, threads=None):
+def cpu_run(kind, L, w0, h0, steps, warmup, threads=None, keep_outputs=False):
     """Time `steps` whole-pair runs of the CPU checker (match_pair: pyramid + all levels + cloud)."""
     from oracle import pyoracle
     from reconstruction_b200 import synth
@@ -145,8 +145,18 @@ def cpu_run(kind, L, w0, h0, steps, warmup, threads=None):
         os.close(devnull)
         os.close(saved)
     W, H = sp.top_size
-    return {"mpix_s": W * H * steps / dt / 1e6, "pts_s": n * steps / dt, "sec_per_step": dt / steps, "cores": cores,
-            "sample": f"{steps} x one synthetic pair {W}x{H}, {L}-level pyramid, all stages + DisparityToCloud"}
+    res = {"mpix_s": W * H * steps / dt / 1e6, "pts_s": n * steps / dt, "sec_per_step": dt / steps, "cores": cores,
+           "sample": f"{steps} x one synthetic pair {W}x{H}, {L}-level pyramid, all stages + DisparityToCloud"}
+    if keep_outputs:  # for the parity block: the checker's final maps and points of this very pair
+        import numpy as np
+
+        xyz = np.empty((n, 3))
+        if n:
+            import ctypes
+
+            o._f("get_points", None, [ctypes.c_void_p] * 2)(o.h, xyz.ctypes.data_as(ctypes.c_void_p))
+        res["outputs"] = {"pair": sp, "d": [o.get_disparity(k, L - 1) for k in (0, 1)], "xyz": xyz}
+    return res
 
 
 def pick_cpu_kind():
@@ -166,25 +176,40 @@ def run_reference(args):
     if rank != 0:
         return 0
     kind, label = pick_cpu_kind()
-    L = CONFIGS[args.config][0]
+    L, w0f, h0f, _ = CONFIGS[args.config]
     total = args.steps + args.warmup
-    # bounded sample of the workload: same pyramid depth (same sweeps per level), smaller frame, sized so that the
-    # whole run stays within a few minutes (0.24 Mpix/s measured on the GPU box's 16 host threads; half of that assumed)
     ncpu = os.cpu_count() or 8
+    # The reference needs minutes per 4096x3072 pair (OrderConstraint is O(W^2 H), CStereoMatching.cpp:337-364), so each step is a
+    # bounded sample: the same pyramid depth (same sweeps per level), a smaller frame, sized so that the whole run stays within a
+    # few minutes (0.24 Mpix/s measured on the GPU box's 16 host threads; half of that assumed).  Config B is small enough to be
+    # timed at its full frame when the run has few steps.  A second, smaller frame is always timed once as well: the two
+    # per-pixel rates show which way the frame-size bias goes (the smaller frame is FASTER per pixel, so the sampled rate
+    # over-states the reference at the full frame and the GPU / CPU ratio is conservative).
     budget = 150.0 / max(total, 1)  # seconds per step
     est_rate = 0.06e6 * max(ncpu, 8) / 8
+    cands = [(w0f, h0f)] if args.config in ("B", "small") else []
+    cands += [(96, 72), (80, 60), (64, 48), (48, 36), (40, 30), (32, 24)]
     w0, h0 = 32, 24
-    for cand in ((96, 72), (80, 60), (64, 48), (48, 36), (40, 30), (32, 24)):
+    for cand in cands:
         px = (cand[0] << (L - 1)) * (cand[1] << (L - 1))
         if px / est_rate <= budget:
             w0, h0 = cand
             break
     r = cpu_run(kind, L, w0, h0, args.steps, args.warmup, threads=ncpu)  # explicit: torchrun exports OMP_NUM_THREADS=1
+    small = (max(w0 * 2 // 3 // 8 * 8, 24), max(h0 * 2 // 3 // 6 * 6, 18))
+    r2 = cpu_run(kind, L, small[0], small[1], 1, 0, threads=ncpu)
+    same = (w0, h0) == (w0f, h0f)
     out = {
         "impl": "reference", "metric": METRIC, "value": r["mpix_s"], "unit": "Mpix/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": CONFIGS[args.config][3], "pyrm_num": L, "cpu_sample": r["sample"]},
+        "config": {"workload": CONFIGS[args.config][3], "pyrm_num": L, "cpu_sample": r["sample"], "same_config": same,
+                   "why": None if same else (f"the reference needs minutes per {w0f << (L - 1)}x{h0f << (L - 1)} pair; a step times one pair of the same "
+                                            f"{L}-level pyramid at {w0 << (L - 1)}x{h0 << (L - 1)} so that the run ends within minutes"),
+                   "frame_size_bias": {"sample_Mpix_s": r["mpix_s"], "sample_top": [w0 << (L - 1), h0 << (L - 1)],
+                                       "smaller_Mpix_s": r2["mpix_s"], "smaller_top": [small[0] << (L - 1), small[1] << (L - 1)],
+                                       "direction": "per-pixel CPU cost grows with the frame (OrderConstraint O(W^2 H)): the reference is slower per "
+                                                    "pixel at the full frame than at the sampled one, so value over-states it"}},
         "pts_per_s": r["pts_s"], "gpu_launches": 0,
         "cpu_baseline": {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"]},
         "e2e": {"value": r["mpix_s"], "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -206,7 +231,6 @@ def run_ours(args):
     import torch.distributed as dist
 
     from reconstruction_b200 import capi, synth
-    from reconstruction_b200 import exchange as xchg
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -240,21 +264,24 @@ def run_ours(args):
     pin_xyz = [torch.empty((npx, 3), dtype=torch.float64).pin_memory() for _ in range(NC)]
     torch.cuda.synchronize()
 
-    # N > 1: the rank's contexts only snapshot their points; one exchange thread per rank issues the NCCL all-gathers in ticket
-    # order (reconstruction_b200/exchange.py::OrderedPointExchange), so no context ever waits for another rank
-    exchange_on = [world > 1]
-    xch = [None]
+    # N > 1: the exchange step goes through the C ABI (sb200_comm_* / sb200_exchange_*, csrc/comm.cu): the rank's contexts only
+    # snapshot their points; the communicator's exchange thread issues the NCCL collectives (counts, then one grouped un-padded
+    # broadcast per rank) in ticket order on its own low-priority stream, so no context ever waits for another rank.
+    # torch.distributed only carries the unique id, the barriers and the max over ranks of the timings.
+    comm = None
+    if world > 1 and not args.no_exchange:
+        box = [capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = capi.PointComm(local, rank, world, box[0], producers=NC, slots=2)
+    xch = [None]      # the communicator while a timed region with the exchange is running
+    seq_base = [0]    # tickets are numbered over the communicator's lifetime
 
     def exchange(k, seq, n_local):
-        """All-gather of the per-pair point buffers over NCCL, overlapped with the following pairs' matching; the last ones are
+        """Snapshot of the pair's points for the all-gather, overlapped with the following pairs' matching; the last gathers are
         waited for inside the timed region."""
         if xch[0] is None:
             return
-        xp, bp, pp, _ = gs[k].points_device()
-        xyz = torch.as_tensor(_DevArr(xp, (npx, 3), "<f8"), device="cuda")
-        bgr = torch.as_tensor(_DevArr(bp, (npx, 3), "|u1"), device="cuda")
-        pix = torch.as_tensor(_DevArr(pp, (npx,), "<i4"), device="cuda")
-        xch[0].submit(k, seq, xyz, bgr, pix, n_local)
+        xch[0].submit(gs[k], k, seq_base[0] + seq)
 
     def step_resident(k, i):
         sp = pairs[(i + k) % 2]
@@ -286,7 +313,7 @@ def run_ours(args):
                 gs[k].stage_ms(reset=True)
                 gs[k].refine_profile(reset=True)
         launches0 = sum(gs[k].launch_count() for k in ctxs)
-        xch[0] = xchg.OrderedPointExchange(len(ctxs), steps * len(ctxs)) if (exchange_on[0] and len(ctxs) == NC) else None
+        xch[0] = comm if (comm is not None and len(ctxs) == NC) else None
         npts = [0] * NC
         errs = []
 
@@ -297,8 +324,6 @@ def run_ours(args):
                         npts[k] = step_fn(k, i)
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
-                if xch[0] is not None:
-                    xch[0].abort(e)
 
         barrier()
         lead = streams[ctxs[0]]
@@ -315,7 +340,8 @@ def run_ours(args):
             raise errs[0]
         with torch.cuda.stream(lead):
             if xch[0] is not None:
-                xch[0].finish()  # the last steps' gathers complete inside the timed region
+                seq_base[0] += steps
+                xch[0].drain(seq_base[0] * NC)  # the last steps' gathers complete inside the timed region
             for k in ctxs[1:]:
                 lead.wait_stream(streams[k])
             ev1.record(lead)
@@ -340,14 +366,16 @@ def run_ours(args):
     single_ms, n_pts, single_launches = None, 0, 0
     if NC > 1:
         single_ms, n_pts, single_launches = timed(step_resident, args.steps, [0], profile=True)  # the matcher alone, no exchange
-    if world > 1:
+    if comm is not None:
         timed(step_resident, 1, every)  # untimed: the exchange's staging and gather buffers get allocated here
+        comm.stats(reset=True)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     # (2) the headline: NC pairs in flight per GPU
     ms, n_pts2, launches = timed(step_resident, args.steps, every, profile=(NC == 1))
     clocks = sampler.stop() if rank == 0 else None
+    xstats = comm.stats(reset=True) if comm is not None else None
     n_pts = n_pts or n_pts2
     stage_ms = g.stage_ms(reset=True)
     ncc_ms = g.stage_level_ms(2, L - 1)  # HighLevelInitialMatch at the top level, both directions
@@ -464,7 +492,13 @@ def run_ours(args):
                                           "concurrently, as the C++ CStereoMatching mirror does (SB200_CTX_PER_DEVICE)",
                        "top_size": [W, H], "pyrm_num": L,
                        "l2": f"inputs larger than L2: ~{2.4 * NC:.1f} GB working set per step, two alternating input pairs",
-                       "exchange": "all-gather of point buffers over NCCL, overlapped with the next pair's matching" if world > 1 else "none (1 GPU)"},
+                       "exchange": ("none (1 GPU)" if world == 1 else "off (--no-exchange: A/B run)" if comm is None else
+                                    "sb200_exchange_submit / sb200_exchange_drain (C ABI): NCCL all-gather of the counts + one grouped "
+                                    "un-padded broadcast per rank, overlapped with the next pair's matching")},
+            "exchange": None if xstats is None else {
+                "collective_ms_per_step": xstats["collective_ms"] / args.steps, "bytes_received_per_step": xstats["bytes_received"] // args.steps,
+                "exchanges_per_step": xstats["exchanges"] / args.steps, "nccl_max_ctas": int(os.environ.get("SB200_NCCL_MAX_CTAS", "4")),
+                "what": "device time of the collectives on this rank's exchange stream (CUDA events), rank 0; they run beside the matching"},
             "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
             "gpu_launches": tot_launch,
             "e2e": {"value": world * NC * npx * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s",
@@ -501,10 +535,32 @@ def run_ours(args):
             kind, label = pick_cpu_kind()
             ncpu = os.cpu_count() or 8
             w0c, h0c = (64, 48) if ncpu < 16 else (96, 72)  # ~10-30 s of CPU work
-            r = cpu_run(kind, L, w0c, h0c, 1, 0, threads=ncpu)
+            r = cpu_run(kind, L, w0c, h0c, 1, 0, threads=ncpu, keep_outputs=True)
             out["cpu_baseline"] = {"value": r["mpix_s"], "unit": "Mpix/s", "cores": r["cores"], "kind": label, "sample": r["sample"],
                                    "sec": r["sec_per_step"]}
+            # parity: the pair the CPU arm just processed, through the CUDA path, compared bit for bit (the checker's outputs are
+            # only read here; nothing measured above depends on them)
+            try:
+                import numpy as np
+
+                ro = r["outputs"]
+                spc = ro["pair"]
+                gp = capi.StereoB200(L, w0c, h0c, device=local)
+                gp.set_pair(*spc.image, *spc.mask)
+                gp.set_calib(spc.Q, spc.R_final, spc.T_final)
+                ng = gp.match_pair()
+                diff = sum(int((gp.get_disparity(k).view(np.int64) != ro["d"][k].view(np.int64)).sum()) for k in (0, 1))
+                gx, _, _ = gp.get_points(ng)
+                pdiff = -1 if ng != len(ro["xyz"]) else int((gx.view(np.int64) != ro["xyz"].view(np.int64)).any(axis=1).sum())
+                out["parity"] = {"against": label, "config": r["sample"], "px_compared": int(2 * ro["d"][0].size), "px_differing": diff,
+                                 "points_compared": int(len(ro["xyz"])), "points_differing": pdiff, "bar": "bit-exact (f64 maps and xyz)",
+                                 "larger_cases": "tests/test_gpu_baseline_parity.py: every dump point at 2048x1536 L3, 1536x1152 L5, 1504x1008 L5"}
+                gp.close()
+            except Exception as e:  # noqa: BLE001
+                out["parity"] = {"unavailable": str(e)[:200]}
         emit(out)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -519,6 +575,7 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--config", choices=sorted(CONFIGS), default="C")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-exchange", action="store_true", help="N > 1: leave the point all-gather out (A/B measurement of its cost)")
     ap.add_argument("--pairs-in-flight", type=int, default=3, help="camera pairs matched concurrently per GPU (contexts per GPU)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -97,9 +97,16 @@ SB200_API int sb200_pair_set_calib(sb200_ctx* ctx, const double* Q, const double
 SB200_API int sb200_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
                                   int lowest_w, int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q,
                                   double* R_final, double* T_final);
+/* cv::stereoRectify changed between the OpenCV the reference links (2.4.5: the SMALLER focal length of the two cameras, image
+ * corners taken at (nx, ny)) and current OpenCV (4.13: the MEAN focal length, corners at (nx-1, ny-1)).  opencv_compat = 245 or
+ * 413 selects the behaviour; sb200_rectify_calib uses 245 - the reference's own dependency - unless the environment says
+ * SB200_OPENCV_COMPAT=413.  Only the 413 behaviour can be pinned by vectors here (tests/golden/rectify_cv2.npz). */
+SB200_API int sb200_rectify_calib_compat(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
+                                         int lowest_w, int pyrm_num, int opencv_compat, double* R_new, double* P_scaled, double* P_final,
+                                         double* Q, double* R_final, double* T_final);
 /* cv::stereoRectify alone, for pinning against OpenCV vectors. */
-SB200_API int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1,
-                                        double* R2, double* P1, double* P2, double* Q);
+SB200_API int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T,
+                                        int opencv_compat, double* R1, double* R2, double* P1, double* P2, double* Q);
 /* Image half for one view (:144-158) on the device: initUndistortRectifyMap(K, 0, R_new, P_scaled, top size, CV_16SC2), remap
  * (INTER_LINEAR) of the colour image and of the mask, erode of the mask with the 3*2^(L-1) ellipse.  src_* are the ORIGINAL
  * frames (src_w x src_h, interleaved BGR / grey) in host memory; the results land in the context's top-level buffers
@@ -164,8 +171,12 @@ SB200_API int sb200_match_pair_host(sb200_ctx* ctx, const uint8_t* bgr0, const u
  * The stream all kernels of this context are launched on (a cudaStream_t), so callers can time
  * with CUDA events on the launching stream. */
 SB200_API void* sb200_stream(sb200_ctx* ctx);
-/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+/* Number of kernels enqueued by this context since creation (bench.py's gpu_launches).  sb200_match_pair replays the fixed
+ * stage order of a pair (MatchOneLayer x PyrmNum + DisparityToCloud, CStereoMatching.cpp:21-29) as ONE CUDA graph launch whose
+ * nodes are these kernels; sb200_graph_info counts the graph launches and how often the executable graph had to be rebuilt
+ * rather than updated in place. */
 SB200_API int64_t sb200_launch_count(const sb200_ctx* ctx);
+SB200_API int sb200_graph_info(const sb200_ctx* ctx, int64_t* graph_launches, int64_t* graph_instantiations);
 /* Accumulated device time (ms, CUDA events) per stage id 0..15 since the last reset; index 0 is the
  * pyramid build, 1-10 the MatchOneLayer stages, 11 the triangulation.  Enabled by
  * sb200_set_profiling(ctx, 1); adds an event pair around each stage. */

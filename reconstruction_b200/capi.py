@@ -28,10 +28,10 @@ SYMBOLS = [
     "sb200_pair_stage_device", "sb200_pair_set_calib", "sb200_match_pair", "sb200_match_one_layer", "sb200_run_stage", "sb200_set_refine_iters",
     "sb200_disparity_info", "sb200_get_disparity", "sb200_set_disparity", "sb200_get_rematch_bounds", "sb200_get_level",
     "sb200_get_margin", "sb200_triangulate", "sb200_get_points", "sb200_points_device", "sb200_match_pair_host",
-    "sb200_stream", "sb200_launch_count", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
+    "sb200_stream", "sb200_launch_count", "sb200_graph_info", "sb200_set_profiling", "sb200_get_stage_ms", "sb200_get_refine_counters",
     "sb200_get_refine_profile", "sb200_get_stage_level_ms", "sb200_get_search_counters",
     "sb200_exp_host",
-    "sb200_rectify_calib", "sb200_stereo_rectify_host", "sb200_rectify_view", "sb200_pair_build", "sb200_get_rectify_maps",
+    "sb200_rectify_calib", "sb200_rectify_calib_compat", "sb200_stereo_rectify_host", "sb200_rectify_view", "sb200_pair_build", "sb200_get_rectify_maps",
     "sb200_set_rectify_maps", "sb200_get_remapped_mask",
     "sb200_sink_filter", "sb200_sink_last_error",
     "sb200_comm_unique_id", "sb200_comm_init", "sb200_comm_destroy", "sb200_comm_last_error", "sb200_allgather_points",
@@ -91,6 +91,7 @@ def load():
         "sb200_match_pair_host": (i32, [vp] * 11 + [i64, P(i64)]),
         "sb200_stream": (vp, [vp]),
         "sb200_launch_count": (i64, [vp]),
+        "sb200_graph_info": (i32, [vp, P(i64), P(i64)]),
         "sb200_set_profiling": (i32, [vp, i32]),
         "sb200_get_stage_ms": (i32, [vp, vp, i32]),
         "sb200_get_refine_counters": (i32, [vp, vp, i32]),
@@ -99,7 +100,8 @@ def load():
         "sb200_get_stage_level_ms": (i32, [vp, i32, i32, P(dbl), i32]),
         "sb200_exp_host": (dbl, [dbl]),
         "sb200_rectify_calib": (i32, [vp] * 4 + [i32] * 4 + [vp] * 6),
-        "sb200_stereo_rectify_host": (i32, [vp, vp, i32, i32] + [vp] * 7),
+        "sb200_rectify_calib_compat": (i32, [vp] * 4 + [i32] * 5 + [vp] * 6),
+        "sb200_stereo_rectify_host": (i32, [vp, vp, i32, i32, vp, vp, i32] + [vp] * 5),
         "sb200_rectify_view": (i32, [vp, i32, vp, vp, i32, i32, vp, vp, vp, i32]),
         "sb200_pair_build": (i32, [vp]),
         "sb200_get_rectify_maps": (i32, [vp, vp, vp]),
@@ -303,6 +305,12 @@ class StereoB200:
     def launch_count(self):
         return int(self.lib.sb200_launch_count(self.h))
 
+    def graph_info(self):
+        """(graph launches, graph instantiations) of sb200_match_pair on this context"""
+        a, b = C.c_int64(), C.c_int64()
+        self._ck(self.lib.sb200_graph_info(self.h, C.byref(a), C.byref(b)), "graph_info")
+        return a.value, b.value
+
     def set_profiling(self, on):
         self._ck(self.lib.sb200_set_profiling(self.h, int(on)), "set_profiling")
 
@@ -334,23 +342,29 @@ class StereoB200:
         return out
 
 
-def rectify_calib(K0, Rt0, K1, Rt1, origin, lowest_w, pyrm_num):
-    """Host half of Rectify (no GPU needed): dict with R_new [2,3,3], P_scaled [2,3,4], P_final [2,3,4], Q, R_final, T_final."""
+def rectify_calib(K0, Rt0, K1, Rt1, origin, lowest_w, pyrm_num, opencv_compat=None):
+    """Host half of Rectify (no GPU needed): dict with R_new [2,3,3], P_scaled [2,3,4], P_final [2,3,4], Q, R_final, T_final.
+    opencv_compat: 245 (the OpenCV the reference links) or 413 (the OpenCV the golden vectors were made with); None = the
+    library default (245 unless SB200_OPENCV_COMPAT says otherwise)."""
     a = [np.ascontiguousarray(m, np.float64) for m in (K0, Rt0, K1, Rt1)]
     out = {"R_new": np.zeros((2, 3, 3)), "P_scaled": np.zeros((2, 3, 4)), "P_final": np.zeros((2, 3, 4)), "Q": np.zeros((4, 4)),
            "R_final": np.zeros((3, 3)), "T_final": np.zeros(3)}
-    rc = load().sb200_rectify_calib(*[_p(m) for m in a], int(origin[0]), int(origin[1]), int(lowest_w), int(pyrm_num),
-                                    *[_p(out[k]) for k in ("R_new", "P_scaled", "P_final", "Q", "R_final", "T_final")])
+    outs = [_p(out[k]) for k in ("R_new", "P_scaled", "P_final", "Q", "R_final", "T_final")]
+    if opencv_compat is None:
+        rc = load().sb200_rectify_calib(*[_p(m) for m in a], int(origin[0]), int(origin[1]), int(lowest_w), int(pyrm_num), *outs)
+    else:
+        rc = load().sb200_rectify_calib_compat(*[_p(m) for m in a], int(origin[0]), int(origin[1]), int(lowest_w), int(pyrm_num),
+                                               int(opencv_compat), *outs)
     if rc != 0:
         raise StereoError("rectify_calib: bad argument")
     return out
 
 
-def stereo_rectify_host(K1, K2, size, R, T):
+def stereo_rectify_host(K1, K2, size, R, T, opencv_compat=413):
     a = [np.ascontiguousarray(m, np.float64) for m in (K1, K2, R, T)]
     R1, R2, P1, P2, Q = np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 4)), np.zeros((3, 4)), np.zeros((4, 4))
-    rc = load().sb200_stereo_rectify_host(_p(a[0]), _p(a[1]), int(size[0]), int(size[1]), _p(a[2]), _p(a[3]), _p(R1), _p(R2), _p(P1),
-                                          _p(P2), _p(Q))
+    rc = load().sb200_stereo_rectify_host(_p(a[0]), _p(a[1]), int(size[0]), int(size[1]), _p(a[2]), _p(a[3]), int(opencv_compat), _p(R1),
+                                          _p(R2), _p(P1), _p(P2), _p(Q))
     if rc != 0:
         raise StereoError("stereo_rectify_host: bad argument")
     return R1, R2, P1, P2, Q

@@ -76,12 +76,19 @@ struct sb200_ctx {
   // Rectify scratch (allocated on first use)
   uint8_t *rc_src_img = nullptr, *rc_src_mask = nullptr, *rc_tab = nullptr;
   size_t rc_src_cap = 0;
+  double* rc_starts = nullptr;  // running row values of initUndistortRectifyMap at every 32nd column
   short2* rc_map1 = nullptr;
   unsigned short* rc_map2 = nullptr;
   short* rc_ellipse = nullptr;
   int rc_ks = 0, rc_levels = 0;
   bool rc_maps_given = false;
   int rc_views_done = 0;
+  // CUDA graph of a whole pair (MatchOneLayer x L + DisparityToCloud): the fixed stage order is captured from the stream
+  // and replayed as one graph launch; the next pair re-captures and updates the executable graph in place (same topology,
+  // new grid sizes / margins / tensor maps).  SB200_GRAPH=0, or profiling on, enqueues kernel by kernel instead.
+  bool use_graph = true;
+  cudaGraphExec_t gexec = nullptr;
+  int64_t graph_launches = 0, graph_rebuilds = 0;
   // instrumentation
   int64_t launches = 0;
   bool profiling = false;
@@ -419,6 +426,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(cudaMemsetAsync(c->search_counters, 0, 2 * sizeof(unsigned long long), c->st));
   if (const char* e = getenv("SB200_SCREEN")) c->screen = atoi(e) != 0;
   if (const char* e = getenv("SB200_BAND")) c->band = atoi(e) != 0;
+  if (const char* e = getenv("SB200_GRAPH")) c->use_graph = atoi(e) != 0;
   CK(dalloc(&c->ds_tmp, n + pad));
   for (int k = 0; k < 4; k++) CK(dalloc(&c->f64buf[k], n + pad));
   for (int d = 0; d < 2; d++) {
@@ -463,6 +471,7 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaSetDevice(c->device);
   if (c->st) cudaStreamSynchronize(c->st);
   for (auto& e : c->events) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  if (c->gexec) cudaGraphExecDestroy(c->gexec);
   for (auto& l : c->lv)
     for (int k = 0; k < 2; k++) { cudaFree(l.img[k]); cudaFree(l.mask[k]); }
   cudaFree(c->d_margins);
@@ -479,7 +488,7 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaFree(c->rs[0].counters);
   cudaFree(c->cs.run); cudaFree(c->cs.eroded); cudaFree(c->cs.row_count); cudaFree(c->cs.row_offset);
   cudaFree(c->d_ellipse);
-  cudaFree(c->rc_src_img); cudaFree(c->rc_src_mask); cudaFree(c->rc_tab); cudaFree(c->rc_map1); cudaFree(c->rc_map2); cudaFree(c->rc_ellipse);
+  cudaFree(c->rc_src_img); cudaFree(c->rc_src_mask); cudaFree(c->rc_tab); cudaFree(c->rc_map1); cudaFree(c->rc_map2); cudaFree(c->rc_starts); cudaFree(c->rc_ellipse);
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
   if (c->h_npoints) cudaFreeHost(c->h_npoints);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
@@ -543,6 +552,7 @@ static int rectify_prepare(sb200_ctx* c, size_t src_px) {
     while ((2 << (c->rc_levels - 1)) <= c->rc_ks) c->rc_levels++;
     CK(dalloc(&c->rc_map1, n));
     CK(dalloc(&c->rc_map2, n));
+    CK(dalloc(&c->rc_starts, (size_t)top.h * ((top.w + 31) / 32) * 3));
     CK(dalloc(&c->rc_tab, (size_t)c->rc_levels * n));
     std::vector<short> j12(2 * (size_t)c->rc_ks);
     sb_ellipse_rows(c->rc_ks, j12.data(), j12.data() + c->rc_ks);
@@ -559,20 +569,35 @@ static int rectify_prepare(sb200_ctx* c, size_t src_px) {
   return SB200_OK;
 }
 
-int sb200_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
-                        int lowest_w, int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final,
-                        double* T_final) {
+// which OpenCV's stereoRectify the calibration half follows by default: the reference links 2.4.5 (SB200_OPENCV_COMPAT=413
+// selects the 4.13 behaviour the golden vectors were made with)
+static int default_compat() {
+  const char* e = getenv("SB200_OPENCV_COMPAT");
+  const int v = e ? atoi(e) : 245;
+  return v >= 300 ? 413 : 245;
+}
+
+int sb200_rectify_calib_compat(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
+                               int lowest_w, int pyrm_num, int opencv_compat, double* R_new, double* P_scaled, double* P_final, double* Q,
+                               double* R_final, double* T_final) {
   if (!K0 || !Rt0 || !K1 || !Rt1 || !R_new || !P_scaled || !P_final || !Q || !R_final || !T_final || origin_w <= 0 || origin_h <= 0 ||
-      lowest_w <= 0 || pyrm_num < 1)
+      lowest_w <= 0 || pyrm_num < 1 || (opencv_compat != 245 && opencv_compat != 413))
     return SB200_ERR_BAD_ARG;
-  sb_rectify_calib(K0, Rt0, K1, Rt1, origin_w, origin_h, lowest_w, pyrm_num, R_new, P_scaled, P_final, Q, R_final, T_final);
+  sb_rectify_calib(K0, Rt0, K1, Rt1, origin_w, origin_h, lowest_w, pyrm_num, R_new, P_scaled, P_final, Q, R_final, T_final, opencv_compat);
   return SB200_OK;
 }
 
-int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1,
-                              double* R2, double* P1, double* P2, double* Q) {
-  if (!K1 || !K2 || !R || !T || !R1 || !R2 || !P1 || !P2 || !Q) return SB200_ERR_BAD_ARG;
-  sb_stereo_rectify(K1, K2, nx, ny, R, T, R1, R2, P1, P2, Q);
+int sb200_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h,
+                        int lowest_w, int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final,
+                        double* T_final) {
+  return sb200_rectify_calib_compat(K0, Rt0, K1, Rt1, origin_w, origin_h, lowest_w, pyrm_num, default_compat(), R_new, P_scaled, P_final, Q,
+                                    R_final, T_final);
+}
+
+int sb200_stereo_rectify_host(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, int opencv_compat,
+                              double* R1, double* R2, double* P1, double* P2, double* Q) {
+  if (!K1 || !K2 || !R || !T || !R1 || !R2 || !P1 || !P2 || !Q || (opencv_compat != 245 && opencv_compat != 413)) return SB200_ERR_BAD_ARG;
+  sb_stereo_rectify(K1, K2, nx, ny, R, T, R1, R2, P1, P2, Q, opencv_compat);
   return SB200_OK;
 }
 
@@ -630,7 +655,7 @@ int sb200_rectify_view(sb200_ctx* c, int view, const uint8_t* src_bgr, const uin
     RectifyView rv;
     if (!sb_rectify_inverse(P_scaled, R_new, rv.iR)) { c->err = "singular rectification matrix"; return SB200_ERR_BAD_ARG; }
     rv.fx = K[0]; rv.fy = K[4]; rv.u0 = K[2]; rv.v0 = K[5];
-    c->launches += launch_rectify_maps(top.w, top.h, rv, c->rc_map1, c->rc_map2, c->st);  // :144
+    c->launches += launch_rectify_maps(top.w, top.h, rv, c->rc_starts, c->rc_map1, c->rc_map2, c->st);  // :144
   }
   c->launches += launch_remap(c->rc_src_img, src_w, src_h, 3, c->rc_map1, c->rc_map2, top.w, top.h, top.img[view], c->st);  // :154
   c->launches += launch_remap(c->rc_src_mask, src_w, src_h, 1, c->rc_map1, c->rc_map2, top.w, top.h, c->rc_tab, c->st);    // :156
@@ -695,10 +720,53 @@ static int match_pair_async(sb200_ctx* c) {
   return triangulate_impl(c, false);
 }
 
+// match_pair_async captured into a graph and launched once.  Everything match_pair_async enqueues is capturable: kernels,
+// memsets, the async copy of the point count, and the event fork / join of K3's side streams.
+static int match_pair_graph(sb200_ctx* c) {
+  CK(cudaStreamBeginCapture(c->st, cudaStreamCaptureModeThreadLocal));
+  const int rc = match_pair_async(c);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(c->st, &graph);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    (void)cudaGetLastError();
+    return rc;
+  }
+  if (e != cudaSuccess || !graph) {
+    c->err = std::string("stream capture failed: ") + cudaGetErrorString(e);
+    (void)cudaGetLastError();
+    return SB200_ERR_CUDA;
+  }
+  bool fresh = c->gexec == nullptr;
+  if (!fresh) {
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(c->gexec, graph, &info) != cudaSuccess) {  // topology changed (e.g. a level fell back to another path)
+      (void)cudaGetLastError();
+      cudaGraphExecDestroy(c->gexec);
+      c->gexec = nullptr;
+      fresh = true;
+    }
+  }
+  if (fresh) {
+    const cudaError_t ei = cudaGraphInstantiate(&c->gexec, graph, 0);
+    if (ei != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      c->gexec = nullptr;
+      c->err = std::string("cudaGraphInstantiate failed: ") + cudaGetErrorString(ei);
+      return SB200_ERR_CUDA;
+    }
+    c->graph_rebuilds++;
+  }
+  cudaGraphDestroy(graph);
+  CK(cudaGraphLaunch(c->gexec, c->st));
+  c->graph_launches++;
+  return SB200_OK;
+}
+
 int sb200_match_pair(sb200_ctx* c, int64_t* n_points) {
   if (!c) return SB200_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  int rc = match_pair_async(c);
+  int rc = (c->use_graph && !c->profiling) ? match_pair_graph(c) : match_pair_async(c);
   if (rc) return rc;
   CK(cudaStreamSynchronize(c->st));
   c->n_points = *c->h_npoints;
@@ -829,6 +897,12 @@ int sb200_match_pair_host(sb200_ctx* c, const uint8_t* bgr0, const uint8_t* bgr1
 
 void* sb200_stream(sb200_ctx* c) { return c ? (void*)c->st : nullptr; }
 int64_t sb200_launch_count(const sb200_ctx* c) { return c ? c->launches : 0; }
+int sb200_graph_info(const sb200_ctx* c, int64_t* graph_launches, int64_t* graph_instantiations) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  if (graph_launches) *graph_launches = c->graph_launches;
+  if (graph_instantiations) *graph_instantiations = c->graph_rebuilds;
+  return SB200_OK;
+}
 
 int sb200_set_profiling(sb200_ctx* c, int enable) {
   if (!c) return SB200_ERR_BAD_ARG;

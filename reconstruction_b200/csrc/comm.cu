@@ -163,7 +163,10 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
   NcclApi& N = nccl();
   Stage& st = c->stage[(size_t)job.producer * c->slots + job.slot];
   Gathered& g = c->out[ticket & 1];
-  CKC(cudaStreamWaitEvent(c->xs, job.ready, 0));
+  if (job.ready) {
+    CKC(cudaStreamWaitEvent(c->xs, job.ready, 0));
+    cudaEventDestroy(job.ready);  // the wait is enqueued; the event's resources go when it has completed
+  }
   // the previous result in this output slot (ticket - 2) must have been consumed: its `done` event precedes us on the same stream
   CKC(cudaEventRecord(g.t0, c->xs));
   const long long mine = job.n;
@@ -307,7 +310,7 @@ void sb200_comm_destroy(sb200_comm* c) {
   c->cv.notify_all();
   if (c->worker.joinable()) c->worker.join();
   if (c->xs) cudaStreamSynchronize(c->xs);
-  for (auto& kv : c->queue) cudaEventDestroy(kv.second.ready);
+  for (auto& kv : c->queue) if (kv.second.ready) cudaEventDestroy(kv.second.ready);
   for (Stage& s : c->stage) { cudaFree(s.xyz); cudaFree(s.bgr); cudaFree(s.pix); if (s.read_done) cudaEventDestroy(s.read_done); }
   for (Gathered& g : c->out) {
     cudaFree(g.xyz); cudaFree(g.bgr); cudaFree(g.pix);
@@ -323,12 +326,15 @@ void sb200_comm_destroy(sb200_comm* c) {
 }
 
 int sb200_exchange_submit(sb200_comm* c, sb200_ctx* ctx, int producer, int64_t seq) {
-  if (!c || !ctx || producer < 0 || producer >= c->producers || seq < 0) return SB200_ERR_BAD_ARG;
+  if (!c || producer < 0 || producer >= c->producers || seq < 0) return SB200_ERR_BAD_ARG;
   void *xyz = nullptr, *bgr = nullptr, *pix = nullptr;
   int64_t n = 0;
-  int rc = sb200_points_device(ctx, &xyz, &bgr, &pix, &n);
-  if (rc) return rc;
-  cudaStream_t ps = (cudaStream_t)sb200_stream(ctx);
+  cudaStream_t ps = nullptr;
+  if (ctx) {  // ctx == NULL: this rank has no pair for this ticket and contributes no points (every rank must take part)
+    int rc = sb200_points_device(ctx, &xyz, &bgr, &pix, &n);
+    if (rc) return rc;
+    ps = (cudaStream_t)sb200_stream(ctx);
+  }
   CKC(cudaSetDevice(c->device));
   const int slot = (int)(seq % c->slots);
   Stage& st = c->stage[(size_t)producer * c->slots + slot];
@@ -338,18 +344,18 @@ int sb200_exchange_submit(sb200_comm* c, sb200_ctx* ctx, int producer, int64_t s
     if (c->failed) return SB200_ERR_CUDA;
     st.busy = true;
   }
-  if (st.has_read) CKC(cudaStreamWaitEvent(ps, st.read_done, 0));  // the gather that read this slot last must be over
-  rc = grow(c, &st.xyz, &st.bgr, &st.pix, &st.cap, n);
-  if (rc) return rc;
+  Job job;
+  job.producer = producer; job.slot = slot; job.n = n;
   if (n > 0) {
+    if (st.has_read) CKC(cudaStreamWaitEvent(ps, st.read_done, 0));  // the gather that read this slot last must be over
+    int rc = grow(c, &st.xyz, &st.bgr, &st.pix, &st.cap, n);
+    if (rc) return rc;
     CKC(cudaMemcpyAsync(st.xyz, xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, ps));
     CKC(cudaMemcpyAsync(st.bgr, bgr, (size_t)n * 3, cudaMemcpyDeviceToDevice, ps));
     CKC(cudaMemcpyAsync(st.pix, pix, (size_t)n * 4, cudaMemcpyDeviceToDevice, ps));
+    CKC(cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
+    CKC(cudaEventRecord(job.ready, ps));
   }
-  Job job;
-  job.producer = producer; job.slot = slot; job.n = n;
-  CKC(cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
-  CKC(cudaEventRecord(job.ready, ps));
   {
     std::lock_guard<std::mutex> lk(c->mu);
     c->queue[seq * c->producers + producer] = job;

@@ -127,12 +127,13 @@ struct RectifyView {
   double iR[9];            // (P[:, :3] * R_new)^-1
   double fx, fy, u0, v0;   // of the ORIGINAL camera matrix
 };
+// compat: 245 = OpenCV 2.4.5's stereoRectify (what the reference links), 413 = OpenCV 4.13's (what the golden vectors pin)
 void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1, double* R2,
-                       double* P1, double* P2, double* Q);
+                       double* P1, double* P2, double* Q, int compat);
 void sb_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h, int lowest_w,
-                      int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final, double* T_final);
+                      int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final, double* T_final, int compat);
 bool sb_rectify_inverse(const double* P_scaled, const double* R_new, double* iR);
-int launch_rectify_maps(int W, int H, const RectifyView& rv, short2* map1, unsigned short* map2, cudaStream_t st);
+int launch_rectify_maps(int W, int H, const RectifyView& rv, double* starts, short2* map1, unsigned short* map2, cudaStream_t st);
 int launch_remap(const uint8_t* src, int sw, int sh, int cn, const short2* map1, const unsigned short* map2, int W, int H, uint8_t* dst,
                  cudaStream_t st);
 int launch_erode_ellipse(uint8_t* tab, int levels, int W, int H, int ks, const short* j12_dev, uint8_t* out, cudaStream_t st);

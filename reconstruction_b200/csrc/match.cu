@@ -299,9 +299,11 @@ __global__ void __launch_bounds__(256) k_ncc_screen_wide(PairViews v, const unsi
     if (!bad) {
       for (int im = lo + gl; im <= hi; im += G) {
         const long ft = (long)y * W + im;
-        // the mask byte and the window rows are requested together (lo >= 2, hi <= W-3: the window is inside the image),
-        // one memory round trip per candidate
+        // narrow ranges (G < 32): the mask byte and the window rows are requested together (lo >= 2, hi <= W-3: the window is
+        // inside the image), one memory round trip per candidate.  Wide ranges mostly run over unmasked columns beyond the
+        // object: there the mask is tested first and the window of an unmasked column is never fetched.
         const unsigned char mk = v.mask1[ft];
+        if (G == 32 && mk != 255) continue;
         int2 sr = make_int2(0, 0);
         if (!ONFLY) sr = v.istat1[ft];
         unsigned q[5][4];

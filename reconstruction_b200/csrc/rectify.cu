@@ -86,8 +86,13 @@ bool inv3(const double* m, double* t) {
 }  // namespace
 
 // stereoRectify for the reference's call (:128-131).  K: 3x3, R: 3x3, T: 3.  Outputs R1, R2 (3x3), P1, P2 (3x4), Q (4x4).
+// compat: which OpenCV's stereoRectify is followed where the versions differ.  245 = OpenCV 2.4.5, the version the reference
+// links (include/opencv/version.hpp:50-53 in the reference tree): the SMALLER of the two focal lengths, image corners at
+// (nx, ny); 413 = OpenCV 4.13, the version the golden vectors were produced with: the MEAN focal length, corners at
+// (nx-1, ny-1).  2.4.5 itself cannot be run here (Windows .lib only), so that branch follows its published source and is not
+// pinned by a vector; the 4.13 branch is (tests/golden/rectify_cv2.npz).
 void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const double* R, const double* T, double* R1, double* R2,
-                       double* P1, double* P2, double* Q) {
+                       double* P1, double* P2, double* Q, int compat) {
   double om[3], r_r[9], t[3], uu[3] = {0, 0, 0}, ww[3], wR[9];
   rodrigues_m2v(R, om);
   for (int i = 0; i < 3; i++) om[i] *= -0.5;  // each camera rotates half way
@@ -108,9 +113,11 @@ void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const
   mat3_mul(wR, r_r, R1, true);  // R1 = wR * r_r^T
   mat3_mul(wR, r_r, R2, false);
   mat3_vec(R2, T, t);
-  // new focal length.  OpenCV 4.13 (the version the golden vectors pin) takes the MEAN of the two f_y (horizontal pair) /
-  // f_x (vertical pair); OpenCV 2.4.5, which the reference linked, took the smaller one.  Zero distortion: no k1 correction.
-  const double fc_new = (K1[(idx ^ 1) * 4] + K2[(idx ^ 1) * 4]) * 0.5;
+  // new focal length from the two f_y (horizontal pair) / f_x (vertical pair): their mean (4.13) or the smaller one (2.4.5).
+  // Zero distortion: no k1 correction.
+  const double f1 = K1[(idx ^ 1) * 4], f2 = K2[(idx ^ 1) * 4];
+  const double fc_new = compat >= 300 ? (f1 + f2) * 0.5 : (f1 < f2 ? f1 : f2);
+  const int cx = compat >= 300 ? nx - 1 : nx, cy = compat >= 300 ? ny - 1 : ny;  // where the far image corners are taken
   // new principal points: the image corners go through undistortPoints / projectPoints in SINGLE precision (CvPoint2D32f)
   double cc[2][2];
   for (int k = 0; k < 2; k++) {
@@ -119,7 +126,7 @@ void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const
     const double ifx = 1. / A[0], ify = 1. / A[4];
     double sx = 0, sy = 0;
     for (int i = 0; i < 4; i++) {
-      const float px = (float)((i % 2) * (nx - 1)), py = (float)((i < 2 ? 0 : 1) * (ny - 1));  // OpenCV >= 3: corners at nx-1, ny-1
+      const float px = (float)((i % 2) * cx), py = (float)((i < 2 ? 0 : 1) * cy);
       const float xn = (float)(((double)px - A[2]) * ifx), yn = (float)(((double)py - A[5]) * ify);  // undistortPoints, k = 0
       const double X = Rk[0] * xn + Rk[1] * yn + Rk[2], Y = Rk[3] * xn + Rk[4] * yn + Rk[5], Z = Rk[6] * xn + Rk[7] * yn + Rk[8];
       const double iz = Z ? 1. / Z : 1.;
@@ -148,7 +155,7 @@ void sb_stereo_rectify(const double* K1, const double* K2, int nx, int ny, const
 
 // The calibration half of Rectify (:121-145): everything the image half and DisparityToCloud need.
 void sb_rectify_calib(const double* K0, const double* Rt0, const double* K1, const double* Rt1, int origin_w, int origin_h, int lowest_w,
-                      int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final, double* T_final) {
+                      int pyrm_num, double* R_new, double* P_scaled, double* P_final, double* Q, double* R_final, double* T_final, int compat) {
   double R0[9], R1m[9], t0[3], t1[3], R[9], T[3], tmp[3];
   for (int i = 0; i < 3; i++) {
     for (int j = 0; j < 3; j++) { R0[i * 3 + j] = Rt0[i * 4 + j]; R1m[i * 3 + j] = Rt1[i * 4 + j]; }
@@ -159,7 +166,7 @@ void sb_rectify_calib(const double* K0, const double* Rt0, const double* K1, con
   mat3_vec(R, t0, tmp);
   for (int i = 0; i < 3; i++) T[i] = -tmp[i] + t1[i];  // T = -R*t0 + t1 (:126)
   double P[2][12];
-  sb_stereo_rectify(K0, K1, origin_w, origin_h, R, T, R_new, R_new + 9, P[0], P[1], Q);
+  sb_stereo_rectify(K0, K1, origin_w, origin_h, R, T, R_new, R_new + 9, P[0], P[1], Q, compat);
   // R_final = R0^T * R_new0^T (:132), T_final = -R0^T * t0 (:133)
   double R0t[9];
   for (int i = 0; i < 3; i++)
@@ -204,18 +211,64 @@ bool sb_rectify_inverse(const double* P_scaled, const double* R_new, double* iR)
 // ------------------------------------------------------------------------------------------------ device
 // initUndistortRectifyMap, zero distortion, m1type CV_16SC2: per destination pixel (j, i) the source position
 //   [x y w]' = iR [j i 1]',  u = fx x/w + u0,  v = fy y/w + v0   in double, then 5-bit fixed point.
-// OpenCV walks a row accumulating x += iR[0] (and its SIMD paths differ again); the closed form used here agrees
-// with it to ~1e-13, i.e. except where u*32 sits within that of a rounding boundary.
-__global__ void __launch_bounds__(256) k_rectify_maps(int W, int H, RectifyView rv, short2* __restrict__ map1, unsigned short* __restrict__ map2) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
-  if (j >= W) return;
+// OpenCV does not evaluate iR [j i 1]' per pixel: it starts a row at (i iR[1] + iR[2], ...) and ADDS iR[0], iR[3], iR[6]
+// once per column, rounding at every step.  A closed form differs from that in the last bits and flips about one map
+// entry in a thousand by one fixed-point step, so the accumulation is reproduced: k_rectify_row_starts walks every row
+// once (one thread per row, three independent chains of additions) and stores the running values at every 32nd column;
+// k_rectify_maps restarts from those and replays 32 additions per thread.  Pinned bit for bit against cv2 4.13's maps
+// (its scalar and its dispatched loop give the same values; tests/golden/rectify_cv2.npz).
+#define SB_RECT_SEG 32
+__global__ void __launch_bounds__(64) k_rectify_row_starts(int W, int H, RectifyView rv, double* __restrict__ starts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= H) return;
   const double* ir = rv.iR;
-  const double _x = (i * ir[1] + ir[2]) + j * ir[0], _y = (i * ir[4] + ir[5]) + j * ir[3], _w = (i * ir[7] + ir[8]) + j * ir[6];
-  const double w = 1. / _w, x = _x * w, y = _y * w;
-  const double u = rv.fx * x + rv.u0, v = rv.fy * y + rv.v0;
-  const int iu = __double2int_rn(u * 32.0), iv = __double2int_rn(v * 32.0);  // saturate_cast<int> = round half to even
-  map1[(size_t)i * W + j] = make_short2((short)(iu >> 5), (short)(iv >> 5));
-  map2[(size_t)i * W + j] = (unsigned short)((iv & 31) * 32 + (iu & 31));
+  double _x = i * ir[1] + ir[2], _y = i * ir[4] + ir[5], _w = i * ir[7] + ir[8];
+  const int nseg = (W + SB_RECT_SEG - 1) / SB_RECT_SEG;
+  double* o = starts + (size_t)i * nseg * 3;
+  for (int sgm = 0; sgm < nseg; sgm++) {
+    o[sgm * 3] = _x; o[sgm * 3 + 1] = _y; o[sgm * 3 + 2] = _w;
+#pragma unroll 8
+    for (int k = 0; k < SB_RECT_SEG; k++) { _x += ir[0]; _y += ir[3]; _w += ir[6]; }
+  }
+}
+
+// one block per row; thread t owns columns [32 t, 32 t + 32); results are staged in shared memory and stored coalesced
+__global__ void __launch_bounds__(128) k_rectify_maps(int W, int H, RectifyView rv, const double* __restrict__ starts,
+                                                      short2* __restrict__ map1, unsigned short* __restrict__ map2) {
+  __shared__ short2 s1[128 * SB_RECT_SEG];
+  __shared__ unsigned short s2[128 * SB_RECT_SEG];
+  const int i = blockIdx.y;
+  const int nseg = (W + SB_RECT_SEG - 1) / SB_RECT_SEG;
+  const double* ir = rv.iR;
+  for (int seg0 = 0; seg0 < nseg; seg0 += 128) {
+    const int sgm = seg0 + threadIdx.x;
+    if (sgm < nseg) {
+      const double* st = starts + ((size_t)i * nseg + sgm) * 3;
+      double _x = st[0], _y = st[1], _w = st[2];
+#pragma unroll 4
+      for (int k = 0; k < SB_RECT_SEG; k++, _x += ir[0], _y += ir[3], _w += ir[6]) {
+        const double w = 1. / _w, x = _x * w, y = _y * w;
+        const double u = rv.fx * x + rv.u0, v = rv.fy * y + rv.v0;
+        const int iu = __double2int_rn(u * 32.0), iv = __double2int_rn(v * 32.0);  // saturate_cast<int> = round half to even
+        // rotated by the thread index: the 32 threads of a warp write 32 different banks
+        const int slot = threadIdx.x * SB_RECT_SEG + ((k + threadIdx.x) & (SB_RECT_SEG - 1));
+        s1[slot] = make_short2((short)(iu >> 5), (short)(iv >> 5));
+        s2[slot] = (unsigned short)((iv & 31) * 32 + (iu & 31));
+      }
+    }
+    __syncthreads();
+    const int j0 = seg0 * SB_RECT_SEG;
+    for (int q = threadIdx.x; q < 128 * SB_RECT_SEG; q += 128) {
+      const int j = j0 + q;
+      if (j < W) {
+        const int t = q / SB_RECT_SEG, k = q % SB_RECT_SEG;
+        const int slot = t * SB_RECT_SEG + ((k + t) & (SB_RECT_SEG - 1));
+        map1[(size_t)i * W + j] = s1[slot];
+        map2[(size_t)i * W + j] = s2[slot];
+      }
+    }
+    __syncthreads();
+  }
 }
 
 // remap, INTER_LINEAR on fixed-point maps: weights (32-fx)(32-fy)*32 ... sum to 2^15; result (sum + 2^14) >> 15.
@@ -272,9 +325,11 @@ __global__ void __launch_bounds__(256) k_erode_ellipse(const uint8_t* __restrict
   out[(size_t)y * W + x] = (uint8_t)v;
 }
 
-int launch_rectify_maps(int W, int H, const RectifyView& rv, short2* map1, unsigned short* map2, cudaStream_t st) {
-  k_rectify_maps<<<dim3((W + 255) / 256, H), 256, 0, st>>>(W, H, rv, map1, map2);
-  return 1;
+// starts: scratch of H * ceil(W / 32) * 3 doubles
+int launch_rectify_maps(int W, int H, const RectifyView& rv, double* starts, short2* map1, unsigned short* map2, cudaStream_t st) {
+  k_rectify_row_starts<<<(H + 63) / 64, 64, 0, st>>>(W, H, rv, starts);
+  k_rectify_maps<<<dim3(1, H), 128, 0, st>>>(W, H, rv, starts, map1, map2);
+  return 2;
 }
 
 int launch_remap(const uint8_t* src, int sw, int sh, int cn, const short2* map1, const unsigned short* map2, int W, int H, uint8_t* dst,

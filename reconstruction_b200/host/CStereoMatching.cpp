@@ -138,7 +138,7 @@ bool CStereoMatching::Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Qo, sbcv::
   return true;
 }
 
-bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& r) {
+bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& r, bool keep_on_device) {
   bool on_device = false;
   if (!Rectify(ctx, CamPair, r.Q, r.Rf, r.Tf, on_device)) {
     r.status = SB200_ERR_BAD_ARG;
@@ -147,13 +147,20 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResul
   }
   std::vector<camera>& cur = m_data->cam[CamPair];
   const size_t cap = (size_t)cur[0].image.rows * cur[0].image.cols;
-  r.xyz.resize(3 * cap);
   const bool want_bgr = m_data->isoutput != 0;  // colours are only used by the PLY branch (:754-756); InsertPoint takes xyz
-  if (want_bgr) r.bgr.resize(3 * cap);
+  if (!keep_on_device) {
+    r.xyz.resize(3 * cap);
+    if (want_bgr) r.bgr.resize(3 * cap);
+  }
   unsigned char* bgr_out = want_bgr ? r.bgr.data() : nullptr;
   // ConstructPyrm, MatchOneLayer x PyrmNum and DisparityToCloud (CStereoMatching.cpp:21-29) on the device
   int rc;
-  if (on_device) {  // frames were rectified in HBM, the pyramid is built: match and fetch the points
+  if (keep_on_device) {  // the points stay in HBM: the caller hands them to the all-gather (sb200_exchange_submit)
+    if (on_device) rc = SB200_OK;
+    else rc = sb200_pair_upload(ctx, cur[0].image.data, cur[1].image.data, cur[0].mask.data, cur[1].mask.data);
+    if (rc == SB200_OK) rc = sb200_pair_set_calib(ctx, r.Q.ptr<double>(), r.Rf.ptr<double>(), r.Tf.ptr<double>());
+    if (rc == SB200_OK) rc = sb200_match_pair(ctx, &r.n);
+  } else if (on_device) {  // frames were rectified in HBM, the pyramid is built: match and fetch the points
     rc = sb200_pair_set_calib(ctx, r.Q.ptr<double>(), r.Rf.ptr<double>(), r.Tf.ptr<double>());
     if (rc == SB200_OK) rc = sb200_match_pair(ctx, &r.n);
     if (rc == SB200_OK) rc = sb200_get_points(ctx, r.xyz.data(), bgr_out, nullptr);
@@ -166,8 +173,10 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResul
     r.error = std::string(sb200_status_string(rc)) + ": " + sb200_last_error(ctx);
     return false;
   }
-  r.xyz.resize(3 * (size_t)r.n);
-  if (want_bgr) r.bgr.resize(3 * (size_t)r.n);
+  if (!keep_on_device) {
+    r.xyz.resize(3 * (size_t)r.n);
+    if (want_bgr) r.bgr.resize(3 * (size_t)r.n);
+  }
   for (int k = 0; k < 2; k++) {  // margin[k] of the top level (:27-28)
     sb200_boundary b;
     sb200_get_margin(ctx, m_data->m_PyrmNum - 1, k, &b);
@@ -175,7 +184,7 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResul
   }
   // the sink's per-pair filter (outlier removal, normals, orientation) on this worker's device, now, while other pairs are
   // still matching; CCloudOptimization::filter(CamPair) appends the stored result when the pairs are handed over in order
-  if (m_CloudOptimization && m_CloudOptimization->sink_enabled && r.n > 0) {
+  if (!keep_on_device && m_CloudOptimization && m_CloudOptimization->sink_enabled && r.n > 0) {
     std::vector<float> rec;
     size_t kept = 0;
     double stats[5] = {0, 0, 0, 0, 0};
@@ -185,6 +194,97 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResul
     // on failure filter(CamPair) retries on the sink's own device and reports
   }
   r.ok = true;
+  return true;
+}
+
+// Several devices, one communicator per device (one host thread each): pair p -> context g = p mod G, context g
+// on device g mod n_dev.  A worker matches its pair and only SNAPSHOTS the points for the exchange (sb200_exchange_submit);
+// ticket (seq, k) gathers the pairs seq*G + k*n_dev + d of the devices d = 0 .. n_dev-1 in that order - pair order - on every
+// device, and device 0's copy is read back once per ticket.  This replaces the reference's serial pair loop feeding the sink
+// (CStereoMatching.cpp:17-33 -> CloudOptimization/CCloudOptimization.cpp:123).  false: NCCL unavailable, nothing was done.
+bool CStereoMatching::GatherPairs(std::vector<sb200_ctx*>& ctxs, const std::vector<int>& ctx_dev, int n_dev, std::vector<PairResult>& results) {
+  const int G = (int)ctxs.size(), P = m_data->m_CampairNum;
+  const int per_dev = (G + n_dev - 1) / n_dev;
+  unsigned char uid[SB200_UNIQUE_ID_BYTES];
+  if (sb200_comm_unique_id(uid) != SB200_OK) {
+    printf("point all-gather unavailable (%s): every worker copies its own points instead\n", sb200_comm_last_error(nullptr));
+    return false;
+  }
+  std::vector<sb200_comm*> comms(n_dev, nullptr);
+  {
+    std::vector<std::thread> th;  // ncclCommInitRank blocks until every rank has joined: one thread per device
+    std::vector<int> rcs(n_dev, 0);
+    for (int d = 0; d < n_dev; d++)
+      th.emplace_back([&, d]() { rcs[d] = sb200_comm_init(&comms[d], ctx_dev[d], d, n_dev, uid, per_dev, 2); });
+    for (auto& t : th) t.join();
+    for (int d = 0; d < n_dev; d++)
+      if (rcs[d] != SB200_OK) {
+        printf("point all-gather unavailable (device %d: %s): every worker copies its own points instead\n", ctx_dev[d],
+               comms[d] ? sb200_comm_last_error(comms[d]) : sb200_status_string(rcs[d]));
+        for (sb200_comm* c : comms) sb200_comm_destroy(c);
+        return false;
+      }
+  }
+  const int64_t n_seq = (P + G - 1) / G, n_tickets = n_seq * per_dev;
+  std::mutex io;
+  std::vector<std::thread> workers;
+  for (int g = 0; g < n_dev * per_dev; g++)
+    workers.emplace_back([&, g]() {
+      const int d = g % n_dev, k = g / n_dev;
+      for (int64_t seq = 0; seq < n_seq; seq++) {
+        const int64_t p = seq * G + g;
+        sb200_ctx* mine = nullptr;
+        if (g < G && p < P) {
+          { std::lock_guard<std::mutex> lk(io); printf("processing pair %d on GPU %d: cam %d and cam %d...\n", (int)p + 1, ctx_dev[g], m_data->cam[p][0].camID, m_data->cam[p][1].camID); }
+          if (RunPair(ctxs[g], ctx_dev[g], (int)p, results[p], true)) mine = ctxs[g];
+        }
+        // every device takes part in every ticket; a device without a pair (or whose pair failed) contributes no points
+        if (sb200_exchange_submit(comms[d], mine, k, seq) != SB200_OK) {
+          std::lock_guard<std::mutex> lk(io);
+          printf("exchange_submit failed on GPU %d: %s\n", ctx_dev[d], sb200_comm_last_error(comms[d]));
+          return;
+        }
+      }
+    });
+  // collector: device 0's gathered buffers, ticket by ticket, split into the pairs by the gathered counts
+  const bool want_bgr = m_data->isoutput != 0;
+  std::vector<int64_t> counts(n_dev);
+  std::vector<double, UninitAllocator<double>> xyz;
+  std::vector<unsigned char, UninitAllocator<unsigned char>> bgr;
+  const size_t cap_px = (size_t)(m_data->m_LowestLevelSize.width << (m_data->m_PyrmNum - 1)) * (m_data->m_LowestLevelSize.height << (m_data->m_PyrmNum - 1));
+  xyz.resize(3 * cap_px * n_dev);
+  if (want_bgr) bgr.resize(3 * cap_px * n_dev);
+  bool ok = true;
+  for (int64_t t = 0; t < n_tickets && ok; t++) {
+    int64_t total = 0;
+    const int rc = sb200_exchange_wait(comms[0], t, counts.data(), xyz.data(), want_bgr ? bgr.data() : nullptr, nullptr, (int64_t)(cap_px * n_dev), &total);
+    if (rc != SB200_OK) {
+      printf("point all-gather failed: %s\n", sb200_comm_last_error(comms[0]));
+      ok = false;
+      break;
+    }
+    const int64_t seq = t / per_dev, k = t % per_dev;
+    size_t off = 0;
+    for (int d = 0; d < n_dev; d++) {
+      const int64_t p = seq * G + k * n_dev + d;
+      const size_t n = (size_t)counts[d];
+      if (p < P && k * n_dev + d < G && results[p].ok) {
+        results[p].xyz.assign(xyz.begin() + 3 * off, xyz.begin() + 3 * (off + n));
+        if (want_bgr) results[p].bgr.assign(bgr.begin() + 3 * off, bgr.begin() + 3 * (off + n));
+        results[p].n = (int64_t)n;
+      }
+      off += n;
+    }
+  }
+  for (auto& w : workers) w.join();
+  double ms = 0;
+  int64_t bytes = 0, nx = 0;
+  sb200_comm_stats(comms[0], &ms, &bytes, &nx, 0);
+  printf("point all-gather: %lld exchanges over %d GPUs, %.1f MB received per GPU, %.2f ms inside the collectives\n", (long long)nx, n_dev, bytes / 1e6, ms);
+  for (sb200_comm* c : comms) sb200_comm_destroy(c);
+  if (!ok)
+    for (auto& r : results)
+      if (r.ok && r.xyz.empty() && r.n > 0) { r.ok = false; r.status = SB200_ERR_CUDA; r.error = "point all-gather failed"; }
   return true;
 }
 
@@ -275,6 +375,9 @@ void CStereoMatching::MatchAllLayer() {
       printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
       RunPair(ctxs[0], ctx_dev[0], p, results[p]);
     }
+  } else if (n_dev > 1 && (allgather >= 0 ? allgather != 0 : !(getenv("SB200_ALLGATHER") && atoi(getenv("SB200_ALLGATHER")) == 0)) &&
+             GatherPairs(ctxs, ctx_dev, n_dev, results)) {
+    // several devices: the points of every pair reached the host through ONE path, the NCCL all-gather of the C ABI
   } else {  // pair p -> context p mod G, context j on device j mod n_dev; each worker owns its context
     std::mutex io;
     std::vector<std::thread> workers;

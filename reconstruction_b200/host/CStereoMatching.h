@@ -30,6 +30,8 @@ class CStereoMatching {
   // --- additions of the mirror (not in the reference) ---
   std::vector<int> devices;        // CUDA devices to use; empty = SB200_DEVICES or every visible device
   int contexts_per_device = 0;     // camera pairs in flight per device; <= 0 = SB200_CTX_PER_DEVICE or 3
+  int allgather = -1;              // several devices: collect the per-pair point buffers with the NCCL all-gather of the C ABI
+                                   // (sb200_exchange_*) instead of one device-to-host copy per worker; < 0 = SB200_ALLGATHER or on
   int decode_threads = 0;          // host threads decoding the input files ahead of the GPU; <= 0 = SB200_DECODE_THREADS or the core count (max 16)
   int last_status = 0;             // sb200 status of the last failing call, 0 if none
   std::string last_error;
@@ -39,7 +41,8 @@ class CStereoMatching {
  private:
   struct PairResult;
   bool Rectify(sb200_ctx* ctx, int CamPair, sbcv::Mat& Q, sbcv::Mat& Rf, sbcv::Mat& Tf, bool& staged_on_device);  // :117-168
-  bool RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& out);
+  bool RunPair(sb200_ctx* ctx, int device, int CamPair, PairResult& out, bool keep_points_on_device = false);
+  bool GatherPairs(std::vector<sb200_ctx*>& ctxs, const std::vector<int>& ctx_dev, int n_dev, std::vector<PairResult>& results);
   sb200_ctx* last_ctx_ = nullptr;
   sbcv::ImagePrefetcher* prefetch_ = nullptr;  // original frames and masks, decoded ahead of the GPU (native Rectify path)
 };

@@ -97,3 +97,26 @@ def test_cli_reads_the_references_image_formats(tmp_path, golden_dir, fmt):
     assert len(xyz) == n and n > 0
     assert np.array_equal(xyz.view(np.int32), pxyz.astype(np.float32).view(np.int32))
     assert np.array_equal(bgr, pbgr)
+
+
+def test_cli_two_gpus_gathers_the_points_over_nccl(tmp_path):
+    """Several devices: the workers keep their points in HBM and the C ABI's NCCL all-gather (sb200_exchange_*) collects them;
+    the merged cloud must equal the single-device run's, byte for byte (pair order, CloudOptimization/CCloudOptimization.cpp:123)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    L, w0, h0, n_pairs = 3, 64, 48, 5  # an odd number of pairs: the last ticket has a device without a pair
+    outs = {}
+    for tag, env in (("one", {"SB200_DEVICES": "0"}), ("two", {"SB200_DEVICES": "0,1", "SB200_CTX_PER_DEVICE": "2"})):
+        d = tmp_path / tag
+        d.mkdir()
+        cfg, _ = stage.write_dataset(str(d), L, w0, h0, n_pairs=n_pairs, isoutput=1)
+        r = subprocess.run([os.path.join(HOST, "reconstruction"), cfg], cwd=str(d), capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout + r.stderr
+        if tag == "two":
+            assert "point all-gather:" in r.stdout, r.stdout
+        outs[tag] = [open(d / f"cloud{p}.ply", "rb").read() for p in range(n_pairs)] + [open(d / "out.ply", "rb").read()]
+    assert outs["one"] == outs["two"]
