@@ -35,6 +35,7 @@ struct sb200_ctx {
   // stream beside its band kernel; fork / join through events (capturable into a CUDA graph)
   cudaStream_t side = nullptr, hole_s[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_hf[2] = {nullptr, nullptr}, ev_hj[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done = nullptr;  // blocking-sync event: host waits sleep instead of spinning (sync_ctx)
   std::vector<Level> lv;
   int* d_margins = nullptr;  // [L][2][4]
   bool uploaded = false, calib_set = false;
@@ -118,6 +119,17 @@ namespace {
   } while (0)
 
 template <class T> cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T)); }
+
+// Wait for the context's stream WITHOUT spinning: an event created with cudaEventBlockingSync puts the host thread to sleep.
+// With several pairs in flight per GPU and one process per GPU there are more waiting host threads than cores on the box
+// (8 ranks x (3 matchers + 1 exchange thread) on 16 hardware threads); spinning waiters then delay the threads that are
+// trying to enqueue work.
+cudaError_t sync_ctx(sb200_ctx* c) {
+  if (!c->ev_done) return cudaStreamSynchronize(c->st);
+  cudaError_t e = cudaEventRecord(c->ev_done, c->st);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(c->ev_done);
+}
 
 struct StageTimer {
   sb200_ctx* c;
@@ -336,7 +348,7 @@ int triangulate_impl(sb200_ctx* c, bool sync) {
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(c->h_npoints, c->d_npoints, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   if (sync) {
-    CK(cudaStreamSynchronize(c->st));
+    CK(sync_ctx(c));
     c->n_points = *c->h_npoints;
   }
   return SB200_OK;
@@ -381,6 +393,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   c->R = radius; c->ws = ws; c->offset = offset;
   *out = c;  // returned even on failure so the caller can read sb200_last_error, then destroy
   CK(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&c->ev_done, cudaEventBlockingSync | cudaEventDisableTiming));
   c->lv.resize(pyrm_num);
   for (int i = 0; i < pyrm_num; i++) {
     Level& l = c->lv[i];
@@ -462,7 +475,7 @@ int sb200_ctx_create(sb200_ctx** out, int device, int pyrm_num, int lowest_w, in
   CK(dalloc(&c->d_npoints, 1));
   CK(cudaMallocHost((void**)&c->h_npoints, sizeof(int)));
   *c->h_npoints = 0;
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -492,6 +505,7 @@ void sb200_ctx_destroy(sb200_ctx* c) {
   cudaFree(c->xyz); cudaFree(c->bgr); cudaFree(c->pix); cudaFree(c->d_npoints);
   if (c->h_npoints) cudaFreeHost(c->h_npoints);
   if (c->side) { cudaStreamSynchronize(c->side); cudaStreamDestroy(c->side); }
+  if (c->ev_done) cudaEventDestroy(c->ev_done);
   if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   if (c->ev_join) cudaEventDestroy(c->ev_join);
   if (c->st) cudaStreamDestroy(c->st);
@@ -511,7 +525,7 @@ static int build_pyramid(sb200_ctx* c) {
   CK(cudaGetLastError());
   std::vector<int> hm((size_t)c->L * 8);
   CK(cudaMemcpyAsync(hm.data(), c->d_margins, hm.size() * sizeof(int), cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   for (int i = 0; i < c->L; i++)
     for (int k = 0; k < 2; k++) {
       const int* m = &hm[(size_t)(i * 2 + k) * 4];
@@ -610,7 +624,7 @@ int sb200_set_rectify_maps(sb200_ctx* c, const int16_t* map1, const uint16_t* ma
   const size_t n = (size_t)top.w * top.h;
   CK(cudaMemcpyAsync(c->rc_map1, map1, n * 4, cudaMemcpyHostToDevice, c->st));
   CK(cudaMemcpyAsync(c->rc_map2, map2, n * 2, cudaMemcpyHostToDevice, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   c->rc_maps_given = true;
   return SB200_OK;
 }
@@ -623,7 +637,7 @@ int sb200_get_rectify_maps(sb200_ctx* c, int16_t* map1, uint16_t* map2) {
   const size_t n = (size_t)top.w * top.h;
   CK(cudaMemcpyAsync(map1, c->rc_map1, n * 4, cudaMemcpyDeviceToHost, c->st));
   CK(cudaMemcpyAsync(map2, c->rc_map2, n * 2, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -633,7 +647,7 @@ int sb200_get_remapped_mask(sb200_ctx* c, uint8_t* out) {
   CK(cudaSetDevice(c->device));
   const Level& top = c->lv[c->L - 1];
   CK(cudaMemcpyAsync(out, c->rc_tab, (size_t)top.w * top.h, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -661,7 +675,7 @@ int sb200_rectify_view(sb200_ctx* c, int view, const uint8_t* src_bgr, const uin
   c->launches += launch_remap(c->rc_src_mask, src_w, src_h, 1, c->rc_map1, c->rc_map2, top.w, top.h, c->rc_tab, c->st);    // :156
   c->launches += launch_erode_ellipse(c->rc_tab, c->rc_levels, top.w, top.h, c->rc_ks, c->rc_ellipse, top.mask[view], c->st);  // :157-158
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   c->uploaded = false;  // the pyramid is stale until sb200_pair_build
   return SB200_OK;
 }
@@ -696,7 +710,7 @@ int sb200_run_stage(sb200_ctx* c, int level, int stage) {
   CK(cudaSetDevice(c->device));
   int rc = run_stage_impl(c, level, stage);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -707,7 +721,7 @@ int sb200_match_one_layer(sb200_ctx* c, int level) {
     int rc = run_stage_impl(c, level, s);
     if (rc) return rc;
   }
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -768,7 +782,7 @@ int sb200_match_pair(sb200_ctx* c, int64_t* n_points) {
   CK(cudaSetDevice(c->device));
   int rc = (c->use_graph && !c->profiling) ? match_pair_graph(c) : match_pair_async(c);
   if (rc) return rc;
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   c->n_points = *c->h_npoints;
   if (n_points) *n_points = c->n_points;
   return SB200_OK;
@@ -795,7 +809,7 @@ int sb200_get_disparity(sb200_ctx* c, int dir, void* host_out) {
   const size_t n = (size_t)c->dw * c->dh;
   const void* src = c->elem == 2 ? (const void*)c->ds[dir] : (const void*)c->dd[dir];
   CK(cudaMemcpyAsync(host_out, src, n * c->elem, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -811,7 +825,7 @@ int sb200_set_disparity(sb200_ctx* c, int dir, const void* host_in, int width, i
     c->dd[dir] = c->f64buf[2 * dir];
     CK(cudaMemcpyAsync(c->dd[dir], host_in, n * 8, cudaMemcpyHostToDevice, c->st));
   }
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   c->dw = width; c->dh = height; c->elem = es;
   return SB200_OK;
 }
@@ -824,7 +838,7 @@ int sb200_get_rematch_bounds(sb200_ctx* c, int dir, int16_t* bl, int16_t* br) {
   const size_t n = (size_t)l.w * l.h;
   CK(cudaMemcpyAsync(bl, c->BL[dir], n * 2, cudaMemcpyDeviceToHost, c->st));
   CK(cudaMemcpyAsync(br, c->BR[dir], n * 2, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -837,7 +851,7 @@ int sb200_get_level(sb200_ctx* c, int level, int view, uint8_t* bgr_out, uint8_t
   const size_t n = (size_t)l.w * l.h;
   if (bgr_out) CK(cudaMemcpyAsync(bgr_out, l.img[view], n * 3, cudaMemcpyDeviceToHost, c->st));
   if (mask_out) CK(cudaMemcpyAsync(mask_out, l.mask[view], n, cudaMemcpyDeviceToHost, c->st));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -867,7 +881,7 @@ int sb200_get_points(sb200_ctx* c, double* xyz_out, uint8_t* bgr_out, int32_t* p
     if (bgr_out) CK(cudaMemcpyAsync(bgr_out, c->bgr, n * 3, cudaMemcpyDeviceToHost, c->st));
     if (pix_out) CK(cudaMemcpyAsync(pix_out, c->pix, n * 4, cudaMemcpyDeviceToHost, c->st));
   }
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   return SB200_OK;
 }
 
@@ -913,7 +927,7 @@ int sb200_set_profiling(sb200_ctx* c, int enable) {
 int sb200_get_stage_ms(sb200_ctx* c, double* ms16, int reset) {
   if (!c || !ms16) return SB200_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   for (auto& e : c->events) {
     float ms = 0;
     if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess && e.stage >= 0 && e.stage < 16) {
@@ -963,7 +977,7 @@ int sb200_get_refine_profile(sb200_ctx* c, int level, double* sweep_ms, int64_t*
 int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
   if (!c || !out2) return SB200_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   unsigned long long h[2];
   CK(cudaMemcpy(h, c->rs[0].counters, sizeof h, cudaMemcpyDeviceToHost));
   out2[1] = (int64_t)h[1];
@@ -977,7 +991,7 @@ int sb200_get_refine_counters(sb200_ctx* c, int64_t* out2, int reset) {
 int sb200_get_search_counters(sb200_ctx* c, int64_t* out2, int reset) {
   if (!c || !out2) return SB200_ERR_BAD_ARG;
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->st));
+  CK(sync_ctx(c));
   unsigned long long h[2];
   CK(cudaMemcpy(h, c->search_counters, sizeof h, cudaMemcpyDeviceToHost));
   out2[0] = (int64_t)h[0];

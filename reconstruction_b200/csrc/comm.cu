@@ -105,6 +105,7 @@ struct sb200_comm {
   int device = 0, rank = 0, nranks = 1, producers = 1, slots = 2;
   ncclComm_t comm = nullptr;
   cudaStream_t xs = nullptr;  // exchange stream
+  cudaEvent_t ev_counts = nullptr;  // blocking-sync event: the exchange thread sleeps while it waits for the counts
   std::vector<Stage> stage;   // [producer * slots + slot]
   Gathered out[2];
   long long* d_counts = nullptr;  // [nranks + 1]: gathered counts, then this rank's count
@@ -173,7 +174,8 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
   CKC(cudaMemcpyAsync(c->d_counts + c->nranks, &mine, sizeof mine, cudaMemcpyHostToDevice, c->xs));
   CKN(N.AllGather(c->d_counts + c->nranks, c->d_counts, 1, ncclInt64, c->comm, c->xs));
   CKC(cudaMemcpyAsync(c->h_counts, c->d_counts, sizeof(long long) * c->nranks, cudaMemcpyDeviceToHost, c->xs));
-  CKC(cudaStreamSynchronize(c->xs));  // the only host-blocking step, and it blocks this thread alone
+  CKC(cudaEventRecord(c->ev_counts, c->xs));
+  CKC(cudaEventSynchronize(c->ev_counts));  // the only host-blocking step; it blocks this thread alone, and sleeping (blocking-sync event)
   g.counts.assign(c->nranks, 0);
   int64_t total = 0;
   for (int r = 0; r < c->nranks; r++) { g.counts[r] = c->h_counts[r]; total += c->h_counts[r]; }
@@ -287,12 +289,13 @@ int sb200_comm_init(sb200_comm** out, int device, int rank, int nranks, const vo
   int lo = 0, hi = 0;
   CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
   CKC(cudaStreamCreateWithPriority(&c->xs, cudaStreamNonBlocking, lo));
+  CKC(cudaEventCreateWithFlags(&c->ev_counts, cudaEventBlockingSync | cudaEventDisableTiming));
   c->stage.resize((size_t)producers * slots);
   for (Stage& s : c->stage) CKC(cudaEventCreateWithFlags(&s.read_done, cudaEventDisableTiming));
   for (Gathered& g : c->out) {
     CKC(cudaEventCreate(&g.t0));
     CKC(cudaEventCreate(&g.t1));
-    CKC(cudaEventCreateWithFlags(&g.done, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&g.done, cudaEventBlockingSync | cudaEventDisableTiming));
   }
   CKC(cudaMalloc((void**)&c->d_counts, sizeof(long long) * (nranks + 1)));
   CKC(cudaMallocHost((void**)&c->h_counts, sizeof(long long) * nranks));
@@ -318,6 +321,7 @@ void sb200_comm_destroy(sb200_comm* c) {
     if (g.t1) cudaEventDestroy(g.t1);
     if (g.done) cudaEventDestroy(g.done);
   }
+  if (c->ev_counts) cudaEventDestroy(c->ev_counts);
   cudaFree(c->d_counts);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->comm) nccl().CommDestroy(c->comm);
