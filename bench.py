@@ -94,13 +94,23 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def wait_first(self, timeout=10.0):
+        """Block until nvidia-smi has delivered its first sample (its start-up is then over)."""
+        t0 = time.time()
+        while self.proc is not None and not self.lines and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """Samples taken from now on belong to the timed region."""
+        self.first = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "first", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -242,7 +252,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # torch.distributed is only the launcher-side bootstrap here (unique id, barriers, max / sum of a few scalars); the data
+        # path's collective is NCCL inside the library (sb200_comm_*).  SB200_BENCH_TORCH_BACKEND=gloo keeps torch off the GPUs.
+        backend = os.environ.get("SB200_BENCH_TORCH_BACKEND", "nccl")
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+    red_dev = "cuda" if (world > 1 and os.environ.get("SB200_BENCH_TORCH_BACKEND", "nccl") == "nccl") else "cpu"
     capi.load()  # raises if libstereo_b200.so was not built
 
     L, w0, h0, desc = CONFIGS[args.config]
@@ -272,7 +289,7 @@ def run_ours(args):
     if world > 1 and not args.no_exchange:
         box = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        comm = capi.PointComm(local, rank, world, box[0], producers=NC, slots=2)
+        comm = capi.PointComm(local, rank, world, box[0], producers=NC, slots=int(os.environ.get("SB200_BENCH_SLOTS", "3")))
     xch = [None]      # the communicator while a timed region with the exchange is running
     seq_base = [0]    # tickets are numbered over the communicator's lifetime
 
@@ -299,6 +316,7 @@ def run_ours(args):
         return n
 
     def barrier():
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -317,11 +335,20 @@ def run_ours(args):
         npts = [0] * NC
         errs = []
 
+        trace = os.environ.get("SB200_BENCH_TRACE") == "1"
+
         def work(k):
+            # No torch CUDA state is touched in the worker threads (the C ABI brings its own streams).  A `with torch.cuda.stream(...)`
+            # here restored the thread's previous device - device 0 in a fresh thread - when the first worker finished, which made
+            # every rank but 0 create a CUDA context on GPU 0 inside the timed region: 0.3 - 2 s during which the process's other
+            # CUDA calls stalled (found with SB200_BENCH_TRACE=1 on two GPUs: only rank 1, only the last step, all contexts at once).
             try:
-                with torch.cuda.stream(streams[k]):
-                    for i in range(steps):
-                        npts[k] = step_fn(k, i)
+                for i in range(steps):
+                    t_a = time.perf_counter()
+                    npts[k] = step_fn(k, i)
+                    if trace:
+                        log(f"[trace rank {rank} ctx {k} {step_fn.__name__} step {i}] {1e3 * (time.perf_counter() - t_a):.1f} ms "
+                            f"(graph launches / instantiations {gs[k].graph_info()})")
             except BaseException as e:  # noqa: BLE001
                 errs.append(e)
 
@@ -348,11 +375,16 @@ def run_ours(args):
         barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            t = torch.tensor([ms], dtype=torch.float64, device=red_dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms, npts[ctxs[0]], sum(gs[k].launch_count() for k in ctxs) - launches0
 
+    # The clock sampler (nvidia-smi in loop mode) is started here, before the warm-up, so that its start-up (NVML attaches to every
+    # GPU of the box) is over long before the timed region; only the samples taken inside the timed region are used.
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     every = list(range(NC))
     for k in every:
         with torch.cuda.stream(streams[k]):
@@ -369,9 +401,9 @@ def run_ours(args):
     if comm is not None:
         timed(step_resident, 1, every)  # untimed: the exchange's staging and gather buffers get allocated here
         comm.stats(reset=True)
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.wait_first()
+        sampler.mark()
     # (2) the headline: NC pairs in flight per GPU
     ms, n_pts2, launches = timed(step_resident, args.steps, every, profile=(NC == 1))
     clocks = sampler.stop() if rank == 0 else None
@@ -463,7 +495,7 @@ def run_ours(args):
     tot_pts = n_pts * NC
     tot_launch = launches
     if world > 1:
-        t = torch.tensor([n_pts * NC, launches], dtype=torch.int64, device="cuda")
+        t = torch.tensor([n_pts * NC, launches], dtype=torch.int64, device=red_dev)
         dist.all_reduce(t)
         tot_pts, tot_launch = int(t[0].item()), int(t[1].item())
 
@@ -497,7 +529,7 @@ def run_ours(args):
                                     "un-padded broadcast per rank, overlapped with the next pair's matching")},
             "exchange": None if xstats is None else {
                 "collective_ms_per_step": xstats["collective_ms"] / args.steps, "bytes_received_per_step": xstats["bytes_received"] // args.steps,
-                "exchanges_per_step": xstats["exchanges"] / args.steps, "nccl_max_ctas": int(os.environ.get("SB200_NCCL_MAX_CTAS", "4")),
+                "exchanges_per_step": xstats["exchanges"] / args.steps, "nccl_max_ctas": int(os.environ.get("SB200_NCCL_MAX_CTAS", "8")), "staging_slots": int(os.environ.get("SB200_BENCH_SLOTS", "3")),
                 "what": "device time of the collectives on this rank's exchange stream (CUDA events), rank 0; they run beside the matching"},
             "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
             "gpu_launches": tot_launch,

@@ -242,6 +242,10 @@ SB200_API int sb200_exchange_wait(sb200_comm* comm, int64_t ticket, int64_t* cou
                                   int32_t* pix_host, int64_t capacity, int64_t* total_out);
 SB200_API int sb200_exchange_device(sb200_comm* comm, int64_t ticket, void** xyz_dev, void** bgr_dev, void** pix_dev, int64_t* total);
 SB200_API int sb200_exchange_drain(sb200_comm* comm, int64_t n_tickets);
+/* Flow control for a consumer that reads every result (sb200_exchange_wait for every ticket, in order): when enabled, the exchange
+ * thread overwrites the result of ticket t-2 only after sb200_exchange_wait(t-2) has returned.  Off by default (a producer-only
+ * user such as bench.py never waits for single tickets). */
+SB200_API int sb200_comm_set_consumer(sb200_comm* comm, int enable);
 /* Device time spent inside the collectives (CUDA events on the exchange stream), bytes received, exchanges done. */
 SB200_API int sb200_comm_stats(sb200_comm* comm, double* collective_ms, int64_t* bytes_received, int64_t* n_exchanges, int reset);
 

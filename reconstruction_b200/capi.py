@@ -35,7 +35,7 @@ SYMBOLS = [
     "sb200_set_rectify_maps", "sb200_get_remapped_mask",
     "sb200_sink_filter", "sb200_sink_last_error",
     "sb200_comm_unique_id", "sb200_comm_init", "sb200_comm_destroy", "sb200_comm_last_error", "sb200_allgather_points",
-    "sb200_exchange_submit", "sb200_exchange_wait", "sb200_exchange_device", "sb200_exchange_drain", "sb200_comm_stats",
+    "sb200_exchange_submit", "sb200_exchange_wait", "sb200_exchange_device", "sb200_exchange_drain", "sb200_comm_stats", "sb200_comm_set_consumer",
 ]
 UNIQUE_ID_BYTES = 128
 
@@ -119,6 +119,7 @@ def load():
         "sb200_exchange_device": (i32, [vp, i64, P(vp), P(vp), P(vp), P(i64)]),
         "sb200_exchange_drain": (i32, [vp, i64]),
         "sb200_comm_stats": (i32, [vp, P(dbl), P(i64), P(i64), i32]),
+        "sb200_comm_set_consumer": (i32, [vp, i32]),
     }
     for name, (res, args) in protos.items():
         fn = getattr(lib, name)
@@ -463,6 +464,9 @@ class PointComm:
         if not want_host:
             return counts, n
         return counts, xyz[:n], bgr[:n], pix[:n]
+
+    def set_consumer(self, on=True):
+        self._ck(self.lib.sb200_comm_set_consumer(self.h, int(on)), "comm_set_consumer")
 
     def drain(self, n_tickets: int):
         self._ck(self.lib.sb200_exchange_drain(self.h, n_tickets), "exchange_drain")

@@ -8,8 +8,8 @@
 //
 // The matcher never waits for another rank: a context only SNAPSHOTS its points (device copy on its own stream into a
 // staging slot) and returns; one exchange thread per communicator issues the collectives in ticket order (the same
-// order on every rank) on a dedicated lowest-priority stream, with NCCL's CTA count bounded (SB200_NCCL_MAX_CTAS) so that
-// the collective's kernels take few SMs from the matcher.
+// order on every rank) on a dedicated highest-priority stream, with NCCL's CTA count bounded (SB200_NCCL_MAX_CTAS): the
+// collective's kernels take few SMs from the matcher, but get them at once.
 //
 // NCCL is bound at run time (dlopen "libnccl.so.2"): the library loads and every other entry point works on a machine
 // without NCCL; sb200_comm_* then report the missing library.
@@ -122,6 +122,8 @@ struct sb200_comm {
   double coll_ms = 0;
   int64_t coll_bytes = 0, coll_n = 0;
   int64_t sync_seq = 0;       // sequence counter of sb200_allgather_points
+  bool track_consumer = false;  // the exchange thread reuses a result slot only after sb200_exchange_wait returned for the ticket in it
+  int64_t consumed = 0;       // tickets [0, consumed) have been waited for
 };
 
 namespace {
@@ -164,6 +166,17 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
   NcclApi& N = nccl();
   Stage& st = c->stage[(size_t)job.producer * c->slots + job.slot];
   Gathered& g = c->out[ticket & 1];
+  if (g.ticket >= 0 && !g.timed) {  // the previous occupant (ticket - 2) finished long ago: book its device time before the events are reused
+    if (cudaEventSynchronize(g.t1) == cudaSuccess) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, g.t0, g.t1) == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(c->mu);
+        c->coll_ms += ms;
+      }
+    }
+    (void)cudaGetLastError();
+    g.timed = true;
+  }
   if (job.ready) {
     CKC(cudaStreamWaitEvent(c->xs, job.ready, 0));
     cudaEventDestroy(job.ready);  // the wait is enqueued; the event's resources go when it has completed
@@ -215,6 +228,12 @@ void exchange_thread(sb200_comm* c) {
       c->cv.wait(lk, [&]() { return c->stop || c->queue.count(c->next_ticket) != 0; });
       if (c->queue.count(c->next_ticket) == 0) return;  // stop requested and nothing left in order
       ticket = c->next_ticket;
+      // two results are kept (ticket parity): with a consumer registered, ticket t may only overwrite ticket t-2 once that one
+      // has been handed over (sb200_exchange_wait returned) - flow control towards a consumer slower than the exchange
+      if (c->track_consumer) {
+        c->cv.wait(lk, [&]() { return c->stop || c->consumed >= ticket - 1; });
+        if (c->stop && c->consumed < ticket - 1) return;
+      }
       job = c->queue[ticket];
       c->queue.erase(ticket);
     }
@@ -236,8 +255,12 @@ void exchange_thread(sb200_comm* c) {
 void add_time(sb200_comm* c, Gathered& g) {
   if (g.timed || g.ticket < 0) return;
   float ms = 0;
-  if (cudaEventElapsedTime(&ms, g.t0, g.t1) == cudaSuccess) c->coll_ms += ms;
-  else (void)cudaGetLastError();
+  if (cudaEventElapsedTime(&ms, g.t0, g.t1) == cudaSuccess) {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->coll_ms += ms;
+  } else {
+    (void)cudaGetLastError();
+  }
   g.timed = true;
 }
 
@@ -276,7 +299,7 @@ int sb200_comm_init(sb200_comm** out, int device, int rank, int nranks, const vo
   CKC(cudaSetDevice(device));
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof id);
-  int max_ctas = 4;  // few SMs for the collective: the matcher's dominant kernel is bound by instruction issue
+  int max_ctas = 8;  // few SMs for the collective: the matcher's dominant kernel is bound by instruction issue (measured on two GPUs: 4 -> 766, 8 -> 783 Mpix/s)
   if (const char* e = getenv("SB200_NCCL_MAX_CTAS")) max_ctas = atoi(e);
   if (N.CommInitRankConfig && max_ctas > 0) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
@@ -286,9 +309,12 @@ int sb200_comm_init(sb200_comm** out, int device, int rank, int nranks, const vo
   } else {
     CKN(N.CommInitRank(&c->comm, nranks, id, rank));
   }
+  // Highest priority: the collective's few CTAs (SB200_NCCL_MAX_CTAS) must get SM slots as soon as they are launched.  The
+  // matcher keeps every SM saturated with thousands of queued CTAs; on a LOW-priority stream NCCL's CTAs were only scheduled when
+  // those queues ran dry, the exchange fell behind the producers (two staging slots) and an 8-GPU step took 183 ms instead of 100.
   int lo = 0, hi = 0;
-  CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // lo = numerically largest = lowest priority
-  CKC(cudaStreamCreateWithPriority(&c->xs, cudaStreamNonBlocking, lo));
+  CKC(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = numerically smallest = highest priority
+  CKC(cudaStreamCreateWithPriority(&c->xs, cudaStreamNonBlocking, hi));
   CKC(cudaEventCreateWithFlags(&c->ev_counts, cudaEventBlockingSync | cudaEventDisableTiming));
   c->stage.resize((size_t)producers * slots);
   for (Stage& s : c->stage) CKC(cudaEventCreateWithFlags(&s.read_done, cudaEventDisableTiming));
@@ -391,6 +417,21 @@ int sb200_exchange_wait(sb200_comm* c, int64_t ticket, int64_t* counts_out, doub
     if (bgr_host) CKC(cudaMemcpy(bgr_host, g.bgr, (size_t)g.total * 3, cudaMemcpyDeviceToHost));
     if (pix_host) CKC(cudaMemcpy(pix_host, g.pix, (size_t)g.total * 4, cudaMemcpyDeviceToHost));
   }
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (ticket + 1 > c->consumed) c->consumed = ticket + 1;
+  }
+  c->cv.notify_all();
+  return SB200_OK;
+}
+
+int sb200_comm_set_consumer(sb200_comm* c, int enable) {
+  if (!c) return SB200_ERR_BAD_ARG;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    c->track_consumer = enable != 0;
+  }
+  c->cv.notify_all();
   return SB200_OK;
 }
 

@@ -225,6 +225,7 @@ bool CStereoMatching::GatherPairs(std::vector<sb200_ctx*>& ctxs, const std::vect
         return false;
       }
   }
+  sb200_comm_set_consumer(comms[0], 1);  // device 0's results are read back ticket by ticket: do not let the exchange run ahead of that
   const int64_t n_seq = (P + G - 1) / G, n_tickets = n_seq * per_dev;
   std::mutex io;
   std::vector<std::thread> workers;

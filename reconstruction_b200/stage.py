@@ -46,12 +46,15 @@ def rig_cameras(n_cam, width, height):
     return out
 
 
-def write_dataset(root, pyrm_num, lowest_w, lowest_h, n_pairs=1, isoutput=0, pair_id0=0, origin_scale=1.0, block_style=True):
-    """n_pairs adjacent pairs (i, i+1) of an (n_pairs+1)-camera rig; returns (config path, [StagedPair])."""
+def write_dataset(root, pyrm_num, lowest_w, lowest_h, n_pairs=1, isoutput=0, pair_id0=0, origin_scale=1.0, block_style=True, distinct=None):
+    """n_pairs adjacent pairs (i, i+1) of an (n_pairs+1)-camera rig; returns (config path, [StagedPair]).
+    distinct: synthesise only that many different pairs and repeat them (hard links) - for large throughput data sets."""
     os.makedirs(os.path.join(root, "staged"), exist_ok=True)
     root = os.path.join(os.path.abspath(root), "")
     top_w, top_h = lowest_w << (pyrm_num - 1), lowest_h << (pyrm_num - 1)
-    pairs = [synth.make_pair(lowest_w, lowest_h, pyrm_num, pair_id=pair_id0 + p, origin_scale=origin_scale) for p in range(n_pairs)]
+    n_syn = n_pairs if not distinct else min(distinct, n_pairs)
+    pairs = [synth.make_pair(lowest_w, lowest_h, pyrm_num, pair_id=pair_id0 + p, origin_scale=origin_scale) for p in range(n_syn)]
+    pairs = [pairs[p % n_syn] for p in range(n_pairs)]
     ow, oh = pairs[0].origin_size
     n_cam = n_pairs + 1
     cams = rig_cameras(n_cam, ow, oh)
@@ -85,8 +88,14 @@ def write_dataset(root, pyrm_num, lowest_w, lowest_h, n_pairs=1, isoutput=0, pai
             for k in (0, 1):
                 f.write(_mat(f"P{k}", np.concatenate([cams[p + k][0] @ cams[p + k][1][:, :3], (cams[p + k][0] @ cams[p + k][1][:, 3])[:, None]], axis=1)))
         for k in (0, 1):
-            write_pnm(root + f"staged/pair{p}_view{k}.ppm", sp.image[k])
-            write_pnm(root + f"staged/pair{p}_mask{k}.pgm", sp.mask[k])
+            for what, ext, arr in (("view", "ppm", sp.image[k]), ("mask", "pgm", sp.mask[k])):
+                dst = root + f"staged/pair{p}_{what}{k}.{ext}"
+                if p >= n_syn:  # a repeated pair: link to the first copy
+                    if os.path.exists(dst):
+                        os.remove(dst)
+                    os.link(root + f"staged/pair{p % n_syn}_{what}{k}.{ext}", dst)
+                else:
+                    write_pnm(dst, arr)
     return root + "config.yml", pairs
 
 
