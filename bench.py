@@ -289,7 +289,7 @@ def run_ours(args):
     if world > 1 and not args.no_exchange:
         box = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
-        comm = capi.PointComm(local, rank, world, box[0], producers=NC, slots=int(os.environ.get("SB200_BENCH_SLOTS", "3")))
+        comm = capi.PointComm(local, rank, world, box[0], producers=NC, slots=int(os.environ.get("SB200_BENCH_SLOTS", "2")))
     xch = [None]      # the communicator while a timed region with the exchange is running
     seq_base = [0]    # tickets are numbered over the communicator's lifetime
 
@@ -529,7 +529,7 @@ def run_ours(args):
                                     "un-padded broadcast per rank, overlapped with the next pair's matching")},
             "exchange": None if xstats is None else {
                 "collective_ms_per_step": xstats["collective_ms"] / args.steps, "bytes_received_per_step": xstats["bytes_received"] // args.steps,
-                "exchanges_per_step": xstats["exchanges"] / args.steps, "nccl_max_ctas": int(os.environ.get("SB200_NCCL_MAX_CTAS", "8")), "staging_slots": int(os.environ.get("SB200_BENCH_SLOTS", "3")),
+                "exchanges_per_step": xstats["exchanges"] / args.steps, "nccl_max_ctas": int(os.environ.get("SB200_NCCL_MAX_CTAS", "16")), "staging_slots": int(os.environ.get("SB200_BENCH_SLOTS", "2")),
                 "what": "device time of the collectives on this rank's exchange stream (CUDA events), rank 0; they run beside the matching"},
             "pts_per_s": tot_pts * args.steps / sec, "points_per_pair": n_pts,
             "gpu_launches": tot_launch,

@@ -2,8 +2,8 @@
 // rank holds the points of its own camera pair(s); the sink wants all of them in pair order
 // (CloudOptimization/CCloudOptimization.cpp:123 appends the clouds pair by pair; the reference loops the pairs serially,
 // CStereoMatching.cpp:17-33).  One NCCL communicator per GPU (one process per GPU, or one host thread per GPU inside a
-// process), and per exchanged pair: an all-gather of the counts, then ONE grouped collective in which every rank
-// broadcasts exactly its own points (xyz f64 x3, bgr u8 x3, pixel index i32) into its slice of the gathered buffers —
+// process), and per exchanged pair: an all-gather of the counts, then ONE NCCL group in which every rank sends exactly
+// its own points (xyz f64 x3, bgr u8 x3, pixel index i32) to every other rank's slice of the gathered buffers —
 // nothing is padded to the largest count.
 //
 // The matcher never waits for another rank: a context only SNAPSHOTS its points (device copy on its own stream into a
@@ -38,6 +38,8 @@ struct NcclApi {
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -61,6 +63,8 @@ NcclApi& nccl() {
     SB_SYM(CommDestroy, "ncclCommDestroy")
     SB_SYM(AllGather, "ncclAllGather")
     SB_SYM(Broadcast, "ncclBroadcast")
+    SB_SYM(Send, "ncclSend")
+    SB_SYM(Recv, "ncclRecv")
     SB_SYM(GroupStart, "ncclGroupStart")
     SB_SYM(GroupEnd, "ncclGroupEnd")
     SB_SYM(GetErrorString, "ncclGetErrorString")
@@ -195,19 +199,47 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
   int rc = grow(c, &g.xyz, &g.bgr, &g.pix, &g.cap, total);
   if (rc) return rc;
   g.total = total;
+  // Every rank's block goes to every other rank, un-padded, in ONE group.  Default: direct sends and receives (through the
+  // NVSwitch every pair of GPUs has its own full-bandwidth path, so the 7 + 7 transfers of a rank run side by side; measured at
+  // 8 GPUs, 5.4 GB received per rank and step).  SB200_EXCHANGE_MODE=bcast: one ncclBroadcast per rank and array instead - ring
+  // broadcasts, which at 8 ranks kept the exchange stream busy for longer than a step takes (103 ms per 93 ms step, 0.83 scaling).
+  static const bool use_bcast = getenv("SB200_EXCHANGE_MODE") && strcmp(getenv("SB200_EXCHANGE_MODE"), "bcast") == 0;
+  std::vector<int64_t> offs(c->nranks, 0);
+  for (int r = 1; r < c->nranks; r++) offs[r] = offs[r - 1] + g.counts[r - 1];
   CKN(N.GroupStart());
-  int64_t off = 0;
-  for (int r = 0; r < c->nranks; r++) {
-    const int64_t n = g.counts[r];
-    if (n > 0) {
+  if (use_bcast) {
+    for (int r = 0; r < c->nranks; r++) {
+      const int64_t n = g.counts[r], off = offs[r];
+      if (n <= 0) continue;
       const bool me = r == c->rank;
       CKN(N.Broadcast(me ? (const void*)st.xyz : (const void*)(g.xyz + 3 * off), g.xyz + 3 * off, (size_t)n * 3, ncclDouble, r, c->comm, c->xs));
       CKN(N.Broadcast(me ? (const void*)st.bgr : (const void*)(g.bgr + 3 * off), g.bgr + 3 * off, (size_t)n * 3, ncclUint8, r, c->comm, c->xs));
       CKN(N.Broadcast(me ? (const void*)st.pix : (const void*)(g.pix + off), g.pix + off, (size_t)n, ncclInt32, r, c->comm, c->xs));
     }
-    off += n;
+  } else {
+    const int64_t mine_n = g.counts[c->rank];
+    for (int d = 1; d < c->nranks; d++) {  // peers in a rotated order: rank r talks to r+d and r-d in step d
+      const int to = (c->rank + d) % c->nranks, from = (c->rank - d + c->nranks) % c->nranks;
+      if (mine_n > 0) {
+        CKN(N.Send(st.xyz, (size_t)mine_n * 3, ncclDouble, to, c->comm, c->xs));
+        CKN(N.Send(st.bgr, (size_t)mine_n * 3, ncclUint8, to, c->comm, c->xs));
+        CKN(N.Send(st.pix, (size_t)mine_n, ncclInt32, to, c->comm, c->xs));
+      }
+      const int64_t n = g.counts[from], off = offs[from];
+      if (n > 0) {
+        CKN(N.Recv(g.xyz + 3 * off, (size_t)n * 3, ncclDouble, from, c->comm, c->xs));
+        CKN(N.Recv(g.bgr + 3 * off, (size_t)n * 3, ncclUint8, from, c->comm, c->xs));
+        CKN(N.Recv(g.pix + off, (size_t)n, ncclInt32, from, c->comm, c->xs));
+      }
+    }
   }
   CKN(N.GroupEnd());
+  if (!use_bcast && g.counts[c->rank] > 0) {  // this rank's own block
+    const int64_t n = g.counts[c->rank], off = offs[c->rank];
+    CKC(cudaMemcpyAsync(g.xyz + 3 * off, st.xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, c->xs));
+    CKC(cudaMemcpyAsync(g.bgr + 3 * off, st.bgr, (size_t)n * 3, cudaMemcpyDeviceToDevice, c->xs));
+    CKC(cudaMemcpyAsync(g.pix + off, st.pix, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->xs));
+  }
   CKC(cudaEventRecord(g.t1, c->xs));
   CKC(cudaEventRecord(g.done, c->xs));
   CKC(cudaEventRecord(st.read_done, c->xs));
@@ -299,7 +331,7 @@ int sb200_comm_init(sb200_comm** out, int device, int rank, int nranks, const vo
   CKC(cudaSetDevice(device));
   ncclUniqueId id;
   memcpy(&id, unique_id, sizeof id);
-  int max_ctas = 8;  // few SMs for the collective: the matcher's dominant kernel is bound by instruction issue (measured on two GPUs: 4 -> 766, 8 -> 783 Mpix/s)
+  int max_ctas = 16;  // a bounded share of the SMs for the collective (measured on two GPUs: 4 -> 766, 8 -> 786, 16 -> 795 Mpix/s)
   if (const char* e = getenv("SB200_NCCL_MAX_CTAS")) max_ctas = atoi(e);
   if (N.CommInitRankConfig && max_ctas > 0) {
     ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;

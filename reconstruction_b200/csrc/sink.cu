@@ -131,7 +131,6 @@ __device__ __forceinline__ void sweep_block(const Grid& g, const unsigned* __res
   }
 }
 
-#define SINK_CPL 24        // candidates per lane the register path of the k-nearest search holds (768 per query; the 27-cell block holds ~730 on a surface)
 #define SINK_KEY_CAP 1024  // candidate distances a warp keeps in shared memory between the passes of its radix select
 
 // adds one digit of `key` to the per-warp histogram; lanes with the same digit elect one lane (neighbours share their leading
@@ -172,8 +171,7 @@ struct SumPass {
 
 // mean distance to the mean_k nearest other points (the query itself is the (0-distance) first neighbour, as in PCL)
 __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* __restrict__ keys, const float4* __restrict__ sp, unsigned n_valid,
-                                                       int mean_k, double* __restrict__ mean_dist, unsigned long long* __restrict__ counters,
-                                                       int reg_path) {
+                                                       int mean_k, double* __restrict__ mean_dist, unsigned long long* __restrict__ counters) {
   __shared__ int s_hist[8][256];
   __shared__ unsigned s_keys[8][SINK_KEY_CAP];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -192,66 +190,7 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
       unsigned prefix = 0;
       int rank = want - 1, less = 0, total = 0, staged = -1;  // staged >= 0: that many keys sit in shared memory
       bool enough = true;
-      // ---- register path (the normal case): the 27-cell block holds at most 32 * SINK_CPL candidates.  Lane l keeps the
-      // squared distances of candidates l, l+32, ... in registers (computed once), and the k-th smallest bit pattern is found
-      // by bisection over the 31 value bits with one warp-wide count per bit (__reduce_add_sync) - no histograms, no
-      // shared memory, no second look at the points.  Same T, `less` and sum as the radix select below.
-      unsigned rkey[SINK_CPL];
-      bool in_regs = false;
-      if (R == 1 && reg_path) {
-        const unsigned len = chi - clo;  // lanes 0..8 hold the nine runs
-        unsigned incl = len;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-          const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += t;
-        }
-        const unsigned M = __shfl_sync(0xffffffffu, incl, 8);
-        if (M <= 32u * SINK_CPL) {
-          in_regs = true;
-          total = (int)M;
-          unsigned rs[9], rb[9];  // start index of run r among the candidates, and (first element of run r) - that start
-#pragma unroll
-          for (int r = 0; r < 9; r++) {
-            rs[r] = __shfl_sync(0xffffffffu, incl - len, r);
-            rb[r] = __shfl_sync(0xffffffffu, clo, r) - rs[r];
-          }
-          unsigned mx = 0;
-#pragma unroll
-          for (int t = 0; t < SINK_CPL; t++) {
-            const unsigned gi = (unsigned)lane + 32u * t;
-            rkey[t] = 0xffffffffu;
-            if (gi < M) {
-              unsigned j = gi + rb[0];
-#pragma unroll
-              for (int r = 1; r < 9; r++)
-                if (gi >= rs[r]) j = gi + rb[r];
-              const float4 p = sp[j];
-              rkey[t] = __float_as_uint(dist2(p.x, p.y, p.z, q.x, q.y, q.z));
-              mx = max(mx, rkey[t]);
-            }
-          }
-          if (total < want) {
-            enough = false;
-          } else {
-            mx = __reduce_max_sync(0xffffffffu, mx);
-            unsigned T = 0;
-            for (int bit = 31 - __clz(mx | 1u); bit >= 0; bit--) {  // no key has a bit above the largest key's top bit
-              const unsigned cand = T | (1u << bit);
-              int c = 0;
-#pragma unroll
-              for (int t = 0; t < SINK_CPL; t++) c += rkey[t] < cand;
-              if ((int)__reduce_add_sync(0xffffffffu, (unsigned)c) <= rank) T = cand;
-            }
-            int c = 0;
-#pragma unroll
-            for (int t = 0; t < SINK_CPL; t++) c += rkey[t] < T;
-            less = (int)__reduce_add_sync(0xffffffffu, (unsigned)c);
-            prefix = T;
-          }
-        }
-      }
-      for (int pass = 0; pass < 4 && enough && !in_regs; pass++) {
+      for (int pass = 0; pass < 4 && enough; pass++) {
         for (int b = lane; b < 256; b += 32) hist[b] = 0;
         __syncwarp();
         if (staged >= 0) {  // later passes read the staged distances instead of the points
@@ -307,11 +246,7 @@ __global__ void __launch_bounds__(256) k_sor_mean_dist(Grid g, const unsigned* _
         continue;
       }
       double s = 0;
-      if (in_regs) {
-#pragma unroll
-        for (int t = 0; t < SINK_CPL; t++)
-          if (rkey[t] < T) s += (double)__fsqrt_rn(__uint_as_float(rkey[t]));  // absent slots are 0xffffffff >= T
-      } else if (staged >= 0) {
+      if (staged >= 0) {
         for (int i = lane; i < staged; i += 32) {
           const unsigned key = skeys[i];
           if (key < T) s += (double)__fsqrt_rn(__uint_as_float(key));
@@ -581,8 +516,7 @@ int sink_filter_device(const double* d_xyz, int64_t n, int mean_k, double std_mu
   SK(mem.alloc(&mean_dist, n));
   SK(cudaMemsetAsync(mean_dist, 0, sizeof(double) * n, st));
   const int grid = 148 * 8;
-  static const int reg_path = !(getenv("SB200_SINK_REGPATH") && atoi(getenv("SB200_SINK_REGPATH")) == 0);  // A/B switch
-  k_sor_mean_dist<<<grid, 256, 0, st>>>(gs->g, gs->keys, gs->sp, n_valid, mean_k, mean_dist, counters, reg_path);
+  k_sor_mean_dist<<<grid, 256, 0, st>>>(gs->g, gs->keys, gs->sp, n_valid, mean_k, mean_dist, counters);
   SK(cudaGetLastError());
   SK(cudaMemcpyAsync(h_mean.data(), mean_dist, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
   unsigned long long h_widened = 0;
