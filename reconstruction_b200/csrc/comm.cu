@@ -126,6 +126,9 @@ struct sb200_comm {
   double coll_ms = 0;
   int64_t coll_bytes = 0, coll_n = 0;
   int64_t sync_seq = 0;       // sequence counter of sb200_allgather_points
+  // all-gather mode: this rank's block padded to the largest count (send side) and the padded gathered blocks (receive side)
+  double* sx = nullptr; uint8_t* sbg = nullptr; int* spx = nullptr; int64_t scap = 0;
+  double* px = nullptr; uint8_t* pbg = nullptr; int* ppx = nullptr; int64_t pcap = 0;
   bool track_consumer = false;  // the exchange thread reuses a result slot only after sb200_exchange_wait returned for the ticket in it
   int64_t consumed = 0;       // tickets [0, consumed) have been waited for
 };
@@ -203,11 +206,43 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
   // NVSwitch every pair of GPUs has its own full-bandwidth path, so the 7 + 7 transfers of a rank run side by side; measured at
   // 8 GPUs, 5.4 GB received per rank and step).  SB200_EXCHANGE_MODE=bcast: one ncclBroadcast per rank and array instead - ring
   // broadcasts, which at 8 ranks kept the exchange stream busy for longer than a step takes (103 ms per 93 ms step, 0.83 scaling).
-  static const bool use_bcast = getenv("SB200_EXCHANGE_MODE") && strcmp(getenv("SB200_EXCHANGE_MODE"), "bcast") == 0;
+  // mode: "sendrecv" (default) = one group of direct sends / receives, nothing padded; "allgather" = three ncclAllGather on blocks
+  // padded to the largest count, then device copies that close the gaps (the gathered buffers stay un-padded, rank-major);
+  // "bcast" = one ncclBroadcast per rank and array.  Measured at 8 GPUs, 5.4 GB received per rank and step (config C, three pairs
+  // in flight, 16 CTAs): sendrecv 2950, allgather 2878, bcast 2727 (8 CTAs), NCCL's copy-engine p2p (NCCL_P2P_USE_CUDA_MEMCPY=1)
+  // 2658 Mpix/s; without the exchange 3234 (profiles/r2_bench_n8_*.json).
+  static const int mode = [] {
+    const char* e = getenv("SB200_EXCHANGE_MODE");
+    return !e ? 1 : !strcmp(e, "allgather") ? 0 : !strcmp(e, "bcast") ? 2 : 1;
+  }();
   std::vector<int64_t> offs(c->nranks, 0);
-  for (int r = 1; r < c->nranks; r++) offs[r] = offs[r - 1] + g.counts[r - 1];
-  CKN(N.GroupStart());
-  if (use_bcast) {
+  int64_t nmax = g.counts[0];
+  for (int r = 1; r < c->nranks; r++) { offs[r] = offs[r - 1] + g.counts[r - 1]; nmax = nmax > g.counts[r] ? nmax : g.counts[r]; }
+  if (mode == 0 && c->nranks > 1 && nmax > 0) {
+    rc = grow(c, &c->sx, &c->sbg, &c->spx, &c->scap, nmax);
+    if (rc) return rc;
+    rc = grow(c, &c->px, &c->pbg, &c->ppx, &c->pcap, nmax * c->nranks);
+    if (rc) return rc;
+    const int64_t n = g.counts[c->rank];
+    if (n > 0) {
+      CKC(cudaMemcpyAsync(c->sx, st.xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(c->sbg, st.bgr, (size_t)n * 3, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(c->spx, st.pix, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->xs));
+    }
+    CKN(N.GroupStart());
+    CKN(N.AllGather(c->sx, c->px, (size_t)nmax * 3, ncclDouble, c->comm, c->xs));
+    CKN(N.AllGather(c->sbg, c->pbg, (size_t)nmax * 3, ncclUint8, c->comm, c->xs));
+    CKN(N.AllGather(c->spx, c->ppx, (size_t)nmax, ncclInt32, c->comm, c->xs));
+    CKN(N.GroupEnd());
+    for (int r = 0; r < c->nranks; r++) {  // close the gaps: rank r's rows to their place in the rank-major concatenation
+      const int64_t nr = g.counts[r], off = offs[r];
+      if (nr <= 0) continue;
+      CKC(cudaMemcpyAsync(g.xyz + 3 * off, c->px + 3 * r * nmax, (size_t)nr * 24, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(g.bgr + 3 * off, c->pbg + 3 * r * nmax, (size_t)nr * 3, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(g.pix + off, c->ppx + r * nmax, (size_t)nr * 4, cudaMemcpyDeviceToDevice, c->xs));
+    }
+  } else if (mode == 2) {
+    CKN(N.GroupStart());
     for (int r = 0; r < c->nranks; r++) {
       const int64_t n = g.counts[r], off = offs[r];
       if (n <= 0) continue;
@@ -216,8 +251,10 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
       CKN(N.Broadcast(me ? (const void*)st.bgr : (const void*)(g.bgr + 3 * off), g.bgr + 3 * off, (size_t)n * 3, ncclUint8, r, c->comm, c->xs));
       CKN(N.Broadcast(me ? (const void*)st.pix : (const void*)(g.pix + off), g.pix + off, (size_t)n, ncclInt32, r, c->comm, c->xs));
     }
+    CKN(N.GroupEnd());
   } else {
     const int64_t mine_n = g.counts[c->rank];
+    CKN(N.GroupStart());
     for (int d = 1; d < c->nranks; d++) {  // peers in a rotated order: rank r talks to r+d and r-d in step d
       const int to = (c->rank + d) % c->nranks, from = (c->rank - d + c->nranks) % c->nranks;
       if (mine_n > 0) {
@@ -232,13 +269,13 @@ int gather_one(sb200_comm* c, int64_t ticket, const Job& job) {
         CKN(N.Recv(g.pix + off, (size_t)n, ncclInt32, from, c->comm, c->xs));
       }
     }
-  }
-  CKN(N.GroupEnd());
-  if (!use_bcast && g.counts[c->rank] > 0) {  // this rank's own block
-    const int64_t n = g.counts[c->rank], off = offs[c->rank];
-    CKC(cudaMemcpyAsync(g.xyz + 3 * off, st.xyz, (size_t)n * 24, cudaMemcpyDeviceToDevice, c->xs));
-    CKC(cudaMemcpyAsync(g.bgr + 3 * off, st.bgr, (size_t)n * 3, cudaMemcpyDeviceToDevice, c->xs));
-    CKC(cudaMemcpyAsync(g.pix + off, st.pix, (size_t)n * 4, cudaMemcpyDeviceToDevice, c->xs));
+    CKN(N.GroupEnd());
+    if (mine_n > 0) {  // this rank's own block
+      const int64_t off = offs[c->rank];
+      CKC(cudaMemcpyAsync(g.xyz + 3 * off, st.xyz, (size_t)mine_n * 24, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(g.bgr + 3 * off, st.bgr, (size_t)mine_n * 3, cudaMemcpyDeviceToDevice, c->xs));
+      CKC(cudaMemcpyAsync(g.pix + off, st.pix, (size_t)mine_n * 4, cudaMemcpyDeviceToDevice, c->xs));
+    }
   }
   CKC(cudaEventRecord(g.t1, c->xs));
   CKC(cudaEventRecord(g.done, c->xs));
@@ -380,6 +417,7 @@ void sb200_comm_destroy(sb200_comm* c) {
     if (g.done) cudaEventDestroy(g.done);
   }
   if (c->ev_counts) cudaEventDestroy(c->ev_counts);
+  cudaFree(c->sx); cudaFree(c->sbg); cudaFree(c->spx); cudaFree(c->px); cudaFree(c->pbg); cudaFree(c->ppx);
   cudaFree(c->d_counts);
   if (c->h_counts) cudaFreeHost(c->h_counts);
   if (c->comm) nccl().CommDestroy(c->comm);
