@@ -223,7 +223,14 @@ int run_stage_impl(sb200_ctx* c, int level, int stage) {
           cudaStream_t sd = (band && d == 1) ? c->side : c->st;
           const int n = launch_high_match(make_views(c, level, d == 0), msrc[d], mtgt[d], c->R, c->offset, c->dd[d], c->dw,
                                           c->dh, c->range_lo[d], c->range_hi[d], c->ds[d], (c->screen && c->R == 2) ? (d ? &c->ss1 : &c->ss) : nullptr, band, sd);
-          if (n < 0) { c->err = "unsupported MatchBlockRadius"; return SB200_ERR_BAD_ARG; }
+          if (n < 0) {
+            if (band) {  // join the side stream before leaving (it may be part of a stream capture)
+              cudaEventRecord(c->ev_join, c->side);
+              cudaStreamWaitEvent(c->st, c->ev_join, 0);
+            }
+            c->err = "unsupported MatchBlockRadius";
+            return SB200_ERR_BAD_ARG;
+          }
           c->launches += n;
         }
         if (band) {
