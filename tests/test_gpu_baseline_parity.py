@@ -126,12 +126,14 @@ def small_case(oracle):
     return sp, L, w0, h0, d, xyz
 
 
-@pytest.mark.parametrize("tile,tma,screen", list(itertools.product(range(8), (0, 1), (0, 1))))
+@pytest.mark.parametrize("tile,tma,screen", list(itertools.product(range(8), (0, 1), (0, 1, 2))))
 def test_every_tile_variant_against_the_oracle(lib, small_case, tile, tma, screen):
-    """All 8 tile shapes of the fused refinement x TMA / plain tile loads x integer screening on / off: final maps and points
-    against the oracle, bit for bit (not against each other)."""
+    """All 8 tile shapes of the fused refinement x TMA / plain tile loads x the NCC search path (0 = every candidate in exact
+    arithmetic, 1 = integer screening with the TMA band kernel for K3, 2 = integer screening with the register-resident K3
+    kernel of round 1): final maps and points against the oracle, bit for bit (not against each other)."""
     sp, L, w0, h0, d, oxyz = small_case
-    g = _env_ctx({"SB200_REFINE_TILE": tile, "SB200_REFINE_TMA": tma, "SB200_SCREEN": screen}, L, w0, h0, *sp.origin_size)
+    g = _env_ctx({"SB200_REFINE_TILE": tile, "SB200_REFINE_TMA": tma, "SB200_SCREEN": int(screen > 0), "SB200_BAND": int(screen != 2)},
+                 L, w0, h0, *sp.origin_size)
     g.set_pair(*sp.image, *sp.mask)
     g.set_calib(sp.Q, sp.R_final, sp.T_final)
     n = g.match_pair()

@@ -127,7 +127,10 @@ def test_full_size_properties(lib, oracle, name, L, w0, h0):
     assert tot0 > 0 and bad0 == 0, f"{bad0} of {tot0} surviving pixels of map 0 violate the uniqueness rule"
     assert _check_cloud(g, sp, oracle, L) == n
     # determinism + invariance under the fused refinement's tiling
-    for env in ({}, {"SB200_REFINE_T": 3, "SB200_REFINE_TILE": 0}, {"SB200_REFINE_T": 6, "SB200_REFINE_TILE": 2}, {"SB200_SCREEN": 0}):
+    # ... and under the alternative code paths: no integer screening, the register-resident K3 kernel instead of the TMA band
+    # kernel, kernel-by-kernel enqueueing instead of the CUDA graph
+    for env in ({}, {"SB200_REFINE_T": 3, "SB200_REFINE_TILE": 0}, {"SB200_REFINE_T": 6, "SB200_REFINE_TILE": 2}, {"SB200_SCREEN": 0},
+                {"SB200_BAND": 0}, {"SB200_GRAPH": 0}):
         g2, n2 = _run(sp, L, w0, h0, env)
         assert n2 == n
         for k in (0, 1):
