@@ -545,6 +545,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "k_refine_fused (DisparityRefine: one launch = several Jacobi sweeps of both matching directions, top pyramid level)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
                          "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                         "limiter": "instruction issue, not HBM: 61 FP64 instructions per pixel-sweep (fixed by bit-exactness) hold the dispatch "
+                                    "port two cycles each, plus ~70 others; DRAM moves 0.41x the algorithmic bytes (DESIGN.md 4, 7)",
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_PX_ITER * top_px / top_n if top_n else None,
                          "avg_launch_us": 1e3 * top_ms / top_n if top_n else None, "launches_timed": top_n,
                          "all_levels": {"achieved": achieved_all, "frac": (achieved_all / peak) if achieved_all else None,
@@ -554,7 +556,9 @@ def run_ours(args):
             "ncc_top_level": {"ms_per_step": ncc_ms / prof_steps, "pixels": ncc_px,
                               "achieved_GBps": (12 * ncc_px * prof_steps / (ncc_ms * 1e-3) / 1e9) if ncc_ms > 0 else None,
                               "frac_of_hbm_peak": (12 * ncc_px * prof_steps / (ncc_ms * 1e-3) / 1e9 / peak) if ncc_ms > 0 else None,
-                              "exact_fallback_pixels_per_step": int(counters[0]) // max(prof_steps, 1)},
+                              "exact_fallback_pixels_per_step": int(counters[0]) // max(prof_steps, 1),
+                              "kernel": "k_ncc_band (TMA-staged 16 x 128 band, one 2x2 quad per thread, exact integer keys) + k_hole_ranges + "
+                                        "list kernels; both directions on two streams (DESIGN.md 3.1)"},
             "rectify": rectify,
             "sink_filter": sink,
             "jpeg_decode": decode,
