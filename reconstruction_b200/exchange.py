@@ -1,8 +1,11 @@
 """The one exchange step of the path: after DisparityToCloud every rank holds the points of its own
 camera pair(s); the sink (CloudOptimization) wants all of them, in pair order.  Pairs shard one per rank with no
 other data-path communication, so this is a count all-gather followed by one all-gather of the payload padded to the
-largest count.  Works on whatever device the tensors live on: NCCL over NVLink for CUDA tensors (bench.py, one
-process per GPU), gloo for the CPU tests.
+largest count.  Works on whatever device the tensors live on: NCCL over NVLink for CUDA tensors, gloo for the CPU tests.
+
+Since round 2 the data path does NOT go through this module: the exchange lives behind the C ABI (csrc/comm.cu:
+sb200_comm_* / sb200_exchange_*; bench.py and the C++ CLI call that).  This file stays as the CPU-testable statement of the
+same ticket / staging-slot logic (tests/test_exchange_gloo.py, world size 2 over gloo).
 """
 from __future__ import annotations
 
