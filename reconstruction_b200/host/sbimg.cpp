@@ -18,6 +18,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -45,6 +48,10 @@ struct Huff {
   // canonical decoding tables (ITU T.81 F.2.2.3)
   int mincode[17], maxcode[18], valptr[17];
   uint16_t fast[1 << 11];  // 11-bit look-ahead: (length << 8) | symbol, 0 = longer code
+  // AC tables only: the same 11 bits resolved down to the coefficient when code + value bits fit in them:
+  // (value << 16) | (kind << 12) | (run << 8) | (code length + value bits); kind 1 = coefficient, 2 = end of block, 3 = ZRL
+  // (sixteen zeros), 0 = not resolved here
+  int32_t fast_ac[1 << 11];
   // false: the code-length counts over-subscribe the code space (no prefix code has them; libjpeg's jdhuff.c
   // refuses such a table too) - building the look-ahead table from it would index past its end
   bool build() {
@@ -68,48 +75,94 @@ struct Huff {
       }
       code <<= 1;
     }
+    for (int i = 0; i < (1 << 11); i++) {
+      fast_ac[i] = 0;
+      const int f = fast[i];
+      if (!f) continue;
+      const int len = f >> 8, run = (f >> 4) & 15, size = f & 15;
+      if (size == 0) {
+        if (run == 0) fast_ac[i] = (2 << 12) | len;
+        else if (run == 15) fast_ac[i] = (3 << 12) | len;
+        else fast_ac[i] = (2 << 12) | len;  // an undefined symbol in a sequential scan: ends the block like EOB (decode_block)
+        continue;
+      }
+      if (len + size > 11) continue;
+      const int bits = (i >> (11 - len - size)) & ((1 << size) - 1);
+      const int v = bits + ((((bits >> (size - 1)) & 1) - 1) & (1 - (1 << size)));  // EXTEND
+      fast_ac[i] = (int32_t)((uint32_t)v << 16) | (1 << 12) | (run << 8) | (len + size);
+    }
     return true;
   }
 };
 
+// The entropy-coded data of one scan (T.81 B.1.1.5), handed to the bit reader one restart interval at a time with the stuffed
+// zero bytes removed and eight zero bytes appended - so the reader never looks for 0xFF and may always load 8 bytes.  A piece
+// ends at the first marker of any kind; what a decoder that runs into it sees is zeros (jdhuff.c's "insert_fake_zeros").
+struct EntropySegment {
+  const uint8_t* end = nullptr;   // end of the file
+  const uint8_t* stop = nullptr;  // the 0xFF of the marker that ended the current piece (or `end`)
+  std::vector<uint8_t> buf;
+  size_t len = 0;                 // bytes of the current piece in buf (the padding follows)
+  void load(const uint8_t* p) {
+    buf.clear();
+    for (;;) {
+      const uint8_t* f = p < end ? (const uint8_t*)memchr(p, 0xFF, (size_t)(end - p)) : nullptr;
+      if (!f || f + 1 >= end) {  // ran off the file; a lone trailing 0xFF is not data
+        buf.insert(buf.end(), p, f ? f : end);
+        stop = end;
+        break;
+      }
+      buf.insert(buf.end(), p, f);
+      if (f[1] != 0x00) { stop = f; break; }
+      buf.push_back(0xFF);
+      p = f + 2;
+    }
+    len = buf.size();
+    buf.insert(buf.end(), 8, (uint8_t)0);
+  }
+  void start(const uint8_t* p, const uint8_t* file_end) { end = file_end; load(p); }
+  // the piece after the next RSTn marker, wherever that is (anything in between is skipped, as a resynchronising decoder does)
+  bool next_restart() {
+    const uint8_t* q = stop;
+    while (q + 1 < end && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
+    if (q + 1 >= end) return false;
+    load(q + 2);
+    return true;
+  }
+  // where the marker parser goes on after the scan: the first marker that is neither a stuffed zero nor RSTn
+  const uint8_t* after() const {
+    const uint8_t* q = stop;
+    while (q + 1 < end && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
+    return q;
+  }
+};
+
+// MSB-first reader over one piece of an EntropySegment.  `n` counts the valid bits at the top of `acc` (56..63 after a refill);
+// bits below them are a preview of the bytes at `p` - or zeros past the end of the piece, which is what a decoder that ran into
+// a marker is fed (jdhuff.c's "insert_fake_zeros").
 struct BitReader {
-  const uint8_t* p;
-  const uint8_t* end;
+  const uint8_t* p = nullptr;
+  const uint8_t* end = nullptr;
   uint64_t acc = 0;
   int n = 0;
-  bool hit_marker = false;
+  void open(const EntropySegment& e) {
+    p = e.buf.data();
+    end = p + e.len;
+    acc = 0;
+    n = 0;
+  }
   void fill() {
-    // fast path: eight bytes at once when none of them is 0xFF (no stuffing, no marker) — the common case
-    if (!hit_marker && end - p >= 8 && n <= 56) {
+    if (p < end) {
       uint64_t w;
       memcpy(&w, p, 8);
-      w = __builtin_bswap64(w);
-      const uint64_t x = ~w;  // a 0xFF byte of w is a zero byte of x
-      if (((x - 0x0101010101010101ull) & ~x & 0x8080808080808080ull) == 0) {
-        const int k = (64 - n) >> 3;  // whole bytes that fit (>= 1)
-        acc |= (w >> (64 - 8 * k)) << (64 - n - 8 * k);
-        n += 8 * k;
-        p += k;
-        return;
-      }
+      acc |= __builtin_bswap64(w) >> n;
+      p += (63 - n) >> 3;
     }
-    while (n <= 56) {
-      int b = 0;
-      if (!hit_marker && p < end) {
-        b = *p;
-        if (b == 0xFF) {
-          if (p + 1 < end && p[1] == 0x00) p += 2;
-          else { hit_marker = true; b = 0; }  // a marker: feed zeros until the caller resynchronises
-        } else p++;
-      }
-      acc |= (uint64_t)b << (56 - n);
-      n += 8;
-    }
+    n |= 56;
   }
   int peek(int k) { if (n < k) fill(); return (int)(acc >> (64 - k)); }
   void skip(int k) { acc <<= k; n -= k; }
   int get(int k) { if (k == 0) return 0; const int v = peek(k); skip(k); return v; }
-  void reset() { acc = 0; n = 0; hit_marker = false; }
 };
 
 inline int huff_decode(BitReader& br, const Huff& h) {
@@ -207,6 +260,146 @@ void idct_islow(const int16_t* coef, const uint16_t* q, uint8_t* out, int pitch)
   }
 }
 
+
+#if defined(__SSE2__)
+// SSE2 twin of idct_islow: the same integer algebra regrouped into pmaddwd pairs (z1 = (a + b) * K; t = z1 + a * L  ==
+// a * (K + L) + b * K, exact in integers), eight columns per register, 16-bit lanes between the passes.  It is exact only while
+// every dequantised value and every pass-1 output fits 16 bits and no 32-bit sum wraps; the guard is the block's
+// L1 = sum |coef * q| <= 5600:  |pass-1 output| <= 11363 * L1(column) / 2048 + 1 (11363 = the largest weight of any input in any
+// output of one pass), so a row of pass-1 outputs sums to at most 5.55 * L1 + 8 = 31088 < 2^15, and every 32-bit partial sum of
+// pass 2 stays below 32768 * 31088 < 2^31.  Blocks outside the guard (and tables with entries above 255) take idct_islow.
+inline __m128i pair16(int a, int b) { return _mm_set1_epi32((int)(((uint32_t)(uint16_t)(int16_t)b << 16) | (uint16_t)(int16_t)a)); }
+
+template <int SHIFT, bool FINAL>
+inline void pass8(__m128i v[8]) {
+  const __m128i c26a = pair16(10703, 4433), c26b = pair16(4433, -10704);
+  const __m128i c04a = pair16(8192, 8192), c04b = pair16(8192, -8192);
+  const __m128i c34a = pair16(-6436, 9633), c34b = pair16(9633, 6437);
+  const __m128i c71a = pair16(-4927, -7373), c71b = pair16(-7373, 4926);
+  const __m128i c53a = pair16(-4176, -20995), c53b = pair16(-20995, 4177);
+  const __m128i rnd = _mm_set1_epi32(1 << (SHIFT - 1));
+  const __m128i z3 = _mm_add_epi16(v[7], v[3]), z4 = _mm_add_epi16(v[5], v[1]);
+  __m128i o[8][2];
+  for (int h = 0; h < 2; h++) {
+#define UNPK(a, b) (h ? _mm_unpackhi_epi16(a, b) : _mm_unpacklo_epi16(a, b))
+    const __m128i a26 = UNPK(v[2], v[6]), a04 = UNPK(v[0], v[4]), a34 = UNPK(z3, z4), a71 = UNPK(v[7], v[1]), a53 = UNPK(v[5], v[3]);
+#undef UNPK
+    const __m128i e3 = _mm_madd_epi16(a26, c26a), e2 = _mm_madd_epi16(a26, c26b);
+    const __m128i e0 = _mm_add_epi32(_mm_madd_epi16(a04, c04a), rnd), e1 = _mm_add_epi32(_mm_madd_epi16(a04, c04b), rnd);
+    const __m128i t10 = _mm_add_epi32(e0, e3), t13 = _mm_sub_epi32(e0, e3), t11 = _mm_add_epi32(e1, e2), t12 = _mm_sub_epi32(e1, e2);
+    const __m128i y3 = _mm_madd_epi16(a34, c34a), y4 = _mm_madd_epi16(a34, c34b);
+    const __m128i o0 = _mm_add_epi32(_mm_madd_epi16(a71, c71a), y3), o3 = _mm_add_epi32(_mm_madd_epi16(a71, c71b), y4);
+    const __m128i o1 = _mm_add_epi32(_mm_madd_epi16(a53, c53a), y4), o2 = _mm_add_epi32(_mm_madd_epi16(a53, c53b), y3);
+    o[0][h] = _mm_srai_epi32(_mm_add_epi32(t10, o3), SHIFT); o[7][h] = _mm_srai_epi32(_mm_sub_epi32(t10, o3), SHIFT);
+    o[1][h] = _mm_srai_epi32(_mm_add_epi32(t11, o2), SHIFT); o[6][h] = _mm_srai_epi32(_mm_sub_epi32(t11, o2), SHIFT);
+    o[2][h] = _mm_srai_epi32(_mm_add_epi32(t12, o1), SHIFT); o[5][h] = _mm_srai_epi32(_mm_sub_epi32(t12, o1), SHIFT);
+    o[3][h] = _mm_srai_epi32(_mm_add_epi32(t13, o0), SHIFT); o[4][h] = _mm_srai_epi32(_mm_sub_epi32(t13, o0), SHIFT);
+  }
+  for (int k = 0; k < 8; k++) {
+    if (FINAL) {  // range_limit[x & 1023]: the 10-bit wrap first, then the clamp (done by the caller's packuswb after + 128)
+      const __m128i m = _mm_set1_epi32(1023), b = _mm_set1_epi32(512);
+      o[k][0] = _mm_sub_epi32(_mm_xor_si128(_mm_and_si128(o[k][0], m), b), b);
+      o[k][1] = _mm_sub_epi32(_mm_xor_si128(_mm_and_si128(o[k][1], m), b), b);
+    }
+    v[k] = _mm_packs_epi32(o[k][0], o[k][1]);
+  }
+}
+
+inline void transpose8(__m128i v[8]) {
+  const __m128i a0 = _mm_unpacklo_epi16(v[0], v[1]), a1 = _mm_unpackhi_epi16(v[0], v[1]);
+  const __m128i a2 = _mm_unpacklo_epi16(v[2], v[3]), a3 = _mm_unpackhi_epi16(v[2], v[3]);
+  const __m128i a4 = _mm_unpacklo_epi16(v[4], v[5]), a5 = _mm_unpackhi_epi16(v[4], v[5]);
+  const __m128i a6 = _mm_unpacklo_epi16(v[6], v[7]), a7 = _mm_unpackhi_epi16(v[6], v[7]);
+  const __m128i b0 = _mm_unpacklo_epi32(a0, a2), b1 = _mm_unpackhi_epi32(a0, a2);
+  const __m128i b2 = _mm_unpacklo_epi32(a1, a3), b3 = _mm_unpackhi_epi32(a1, a3);
+  const __m128i b4 = _mm_unpacklo_epi32(a4, a6), b5 = _mm_unpackhi_epi32(a4, a6);
+  const __m128i b6 = _mm_unpacklo_epi32(a5, a7), b7 = _mm_unpackhi_epi32(a5, a7);
+  v[0] = _mm_unpacklo_epi64(b0, b4); v[1] = _mm_unpackhi_epi64(b0, b4);
+  v[2] = _mm_unpacklo_epi64(b1, b5); v[3] = _mm_unpackhi_epi64(b1, b5);
+  v[4] = _mm_unpacklo_epi64(b2, b6); v[5] = _mm_unpackhi_epi64(b2, b6);
+  v[6] = _mm_unpacklo_epi64(b3, b7); v[7] = _mm_unpackhi_epi64(b3, b7);
+}
+
+// false: the block is outside the range in which 16-bit lanes / 32-bit sums are exact -> caller takes the int64 path.
+// q16: the quantisation table as int16 (the caller guarantees every entry <= 255).
+inline bool idct_islow_sse2(const int16_t* coef, const int16_t* q16, uint8_t* out, int pitch) {
+  __m128i v[8], l1 = _mm_setzero_si128();
+  for (int r = 0; r < 8; r++) {
+    const __m128i c = _mm_loadu_si128((const __m128i*)(coef + 8 * r)), q = _mm_loadu_si128((const __m128i*)(q16 + 8 * r));
+    const __m128i a = _mm_max_epi16(c, _mm_subs_epi16(_mm_setzero_si128(), c));
+    l1 = _mm_add_epi32(l1, _mm_madd_epi16(a, q));
+    v[r] = _mm_mullo_epi16(c, q);
+  }
+  l1 = _mm_add_epi32(l1, _mm_shuffle_epi32(l1, 0x4E));
+  l1 = _mm_add_epi32(l1, _mm_shuffle_epi32(l1, 0xB1));
+  if (_mm_cvtsi128_si32(l1) > 5600) return false;
+  pass8<11, false>(v);
+  transpose8(v);
+  pass8<18, true>(v);
+  transpose8(v);
+  const __m128i c128 = _mm_set1_epi16(128);
+  for (int r = 0; r < 8; r += 2) {
+    const __m128i p = _mm_packus_epi16(_mm_add_epi16(v[r], c128), _mm_add_epi16(v[r + 1], c128));
+    _mm_storel_epi64((__m128i*)(out + (size_t)r * pitch), p);
+    _mm_storel_epi64((__m128i*)(out + (size_t)(r + 1) * pitch), _mm_unpackhi_epi64(p, p));
+  }
+  return true;
+}
+#endif
+
+// Per-row loops of the output stage (jdsample.c / jdcolor.c arithmetic, see Jpeg::upsample_row / to_mat).  On x86-64 GCC builds
+// an AVX2 clone next to the baseline one and picks at load time (ifunc): the 32-bit multiplies of the colour conversion only
+// vectorise from SSE4.1 on, and the baseline build is plain SSE2.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define SB_ROW_CLONES __attribute__((target_clones("avx2", "default")))
+#else
+#define SB_ROW_CLONES
+#endif
+SB_ROW_CLONES void ycc_to_bgr_row(const uint8_t* __restrict__ p0, const uint8_t* __restrict__ p1, const uint8_t* __restrict__ p2,
+                                  uint8_t* __restrict__ o, int W) {
+  // jdcolor.c ycc_rgb_convert, SCALEBITS 16: the table entries written out as arithmetic (FIX(1.40200) = 91881,
+  // FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554, ONE_HALF = 32768; arithmetic right shifts)
+  for (int x = 0; x < W; x++) {
+    const int yy = p0[x], cb = p1[x] - 128, cr = p2[x] - 128;
+    int r = yy + ((91881 * cr + 32768) >> 16);
+    int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
+    int b = yy + ((116130 * cb + 32768) >> 16);
+    r = r < 0 ? 0 : (r > 255 ? 255 : r);
+    g = g < 0 ? 0 : (g > 255 ? 255 : g);
+    b = b < 0 ? 0 : (b > 255 ? 255 : b);
+    o[3 * x] = (uint8_t)b; o[3 * x + 1] = (uint8_t)g; o[3 * x + 2] = (uint8_t)r;
+  }
+}
+SB_ROW_CLONES void h2v1_fancy_row(const uint8_t* __restrict__ in, uint8_t* __restrict__ dst, int n) {
+  dst[0] = in[0];
+  dst[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
+  for (int i = 1; i < n - 1; i++) {
+    const int v = in[i] * 3;
+    dst[2 * i] = (uint8_t)((v + in[i - 1] + 1) >> 2);
+    dst[2 * i + 1] = (uint8_t)((v + in[i + 1] + 2) >> 2);
+  }
+  dst[2 * n - 2] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
+  dst[2 * n - 1] = in[n - 1];
+}
+SB_ROW_CLONES void h2v2_fancy_row(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, uint8_t* __restrict__ dst, int n) {
+  dst[0] = (uint8_t)(((in0[0] * 3 + in1[0]) * 4 + 8) >> 4);
+  dst[1] = (uint8_t)(((in0[0] * 3 + in1[0]) * 3 + (in0[1] * 3 + in1[1]) + 7) >> 4);
+  for (int i = 1; i < n - 1; i++) {  // column sums recomputed per column: independent iterations (vectorisable)
+    const int last = in0[i - 1] * 3 + in1[i - 1], cur = in0[i] * 3 + in1[i], next = in0[i + 1] * 3 + in1[i + 1];
+    dst[2 * i] = (uint8_t)((cur * 3 + last + 8) >> 4);
+    dst[2 * i + 1] = (uint8_t)((cur * 3 + next + 7) >> 4);
+  }
+  const int cur = in0[n - 1] * 3 + in1[n - 1], last = in0[n - 2] * 3 + in1[n - 2];
+  dst[2 * n - 2] = (uint8_t)((cur * 3 + last + 8) >> 4);
+  dst[2 * n - 1] = (uint8_t)((cur * 4 + 7) >> 4);
+}
+SB_ROW_CLONES void h1v2_fancy_row(const uint8_t* __restrict__ in0, const uint8_t* __restrict__ in1, uint8_t* __restrict__ dst, int W, int bias) {
+  for (int x = 0; x < W; x++) dst[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
+}
+SB_ROW_CLONES void grey_to_bgr_row(const uint8_t* __restrict__ p0, uint8_t* __restrict__ o, int W) {
+  for (int x = 0; x < W; x++) o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = p0[x];
+}
+
 struct Jpeg {
   const uint8_t* d;
   size_t n;
@@ -218,10 +411,19 @@ struct Jpeg {
   int adobe_transform = -1;
   Comp comp[3];
   uint16_t qt[4][64];
-  bool qt_set[4] = {false, false, false, false};
+  int16_t qt16[4][64];  // the same table for the 16-bit-lane transform; usable when every entry is <= 255 (qt_small)
+  bool qt_set[4] = {false, false, false, false}, qt_small[4] = {false, false, false, false};
   Huff hdc[4], hac[4];
+  EntropySegment ent;  // the scan being decoded
 
   static int be16(const uint8_t* p) { return (p[0] << 8) | p[1]; }
+
+  void idct(const int16_t* coef, int tq, uint8_t* out, int pitch) const {
+#if defined(__SSE2__)
+    if (qt_small[tq] && idct_islow_sse2(coef, qt16[tq], out, pitch)) return;
+#endif
+    idct_islow(coef, qt[tq], out, pitch);
+  }
 
   // Returns the zigzag position of the last non-zero coefficient (0 = DC only), or -1 on corrupt data.  A code and the value
   // bits that follow it (at most 16 + 15 bits) are taken from one look at the 64-bit accumulator.
@@ -235,9 +437,36 @@ struct Jpeg {
     c.pred += diff;
     coef[0] = (int16_t)c.pred;
     int last = 0;
+    // the reader lives in registers across the AC loop and is refilled before every symbol (no data-dependent branch: a
+    // symbol and its value bits take at most 31 of the >= 56 bits a refill leaves)
+    uint64_t acc = br.acc;
+    int n = br.n;
+    const uint8_t* bp = br.p;
+    const uint8_t* const bend = br.end;
     for (int k = 1; k < 64;) {
-      if (br.n < 32) br.fill();
-      const int look = (int)(br.acc >> 48);
+      if (bp < bend) {
+        uint64_t w;
+        memcpy(&w, bp, 8);
+        acc |= __builtin_bswap64(w) >> n;
+        bp += (63 - n) >> 3;
+      }
+      n |= 56;
+      const int look = (int)(acc >> 48);
+      const int32_t fa = ac.fast_ac[look >> 5];
+      if ((fa >> 12) & 3) {  // code and value bits resolved by one look-up
+        const int len = fa & 255, kind = (fa >> 12) & 3;
+        acc <<= len; n -= len;
+        if (kind == 1) {
+          k += (fa >> 8) & 15;
+          if (k > 63) { br.acc = acc; br.n = n; br.p = bp; return -1; }
+          coef[kZigzag[k]] = (int16_t)(fa >> 16);
+          last = k++;
+          continue;
+        }
+        if (kind == 2) break;
+        k += 16;
+        continue;
+      }
       int len, rs;
       const uint16_t f = ac.fast[look >> 5];
       if (f) { len = f >> 8; rs = f & 255; }
@@ -247,32 +476,34 @@ struct Jpeg {
           const int code = look >> (16 - l);
           if (ac.maxcode[l] >= 0 && code <= ac.maxcode[l] && code >= ac.mincode[l]) { len = l; rs = ac.vals[ac.valptr[l] + code - ac.mincode[l]]; break; }
         }
-        if (rs < 0) return -1;
+        if (rs < 0) { br.acc = acc; br.n = n; br.p = bp; return -1; }
       }
       const int r = rs >> 4;
       s = rs & 15;
       if (s == 0) {
-        br.skip(len);
+        acc <<= len; n -= len;
         if (r != 15) break;
         k += 16;
         continue;
       }
       k += r;
-      if (k > 63) return -1;
-      const int bits = (int)((br.acc << len) >> (64 - s));
-      br.skip(len + s);
+      if (k > 63) { br.acc = acc; br.n = n; br.p = bp; return -1; }
+      const int bits = (int)((acc << len) >> (64 - s));
+      acc <<= len + s; n -= len + s;
       coef[kZigzag[k]] = (int16_t)extend(bits, s);
       last = k;
       k++;
     }
+    br.acc = acc; br.n = n; br.p = bp;
     return last;
   }
 
   // one scan: `sc` lists component indices.  Interleaved scans walk MCUs; a single-component scan walks that component's own
   // blocks (ceil(dw / 8) x ceil(dh / 8), T.81 A.2.2)
   bool scan(const uint8_t*& p, const std::vector<int>& sc) {
+    ent.start(p, d + n);
     BitReader br;
-    br.p = p; br.end = d + n;
+    br.open(ent);
     for (int ci : sc) comp[ci].pred = 0;
     const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
     const bool inter = sc.size() > 1;
@@ -283,11 +514,8 @@ struct Jpeg {
     for (int my = 0; my < uy; my++)
       for (int mx = 0; mx < ux; mx++) {
         if (restart && until_restart == 0) {  // expect RSTn
-          br.reset();
-          const uint8_t* q = br.p;
-          while (q + 1 < d + n && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
-          if (q + 1 >= d + n) { err = "missing restart marker"; return false; }
-          br.p = q + 2;
+          if (!ent.next_restart()) { err = "missing restart marker"; return false; }
+          br.open(ent);
           for (int ci : sc) comp[ci].pred = 0;
           until_restart = restart;
         }
@@ -305,18 +533,14 @@ struct Jpeg {
                   const uint8_t v = range_limit(descale((int64_t)coef[0] * qt[c.tq][0] * 4, 5));
                   for (int r = 0; r < 8; r++) memset(dst + (size_t)r * c.pitch, v, 8);
                 } else {
-                  idct_islow(coef, qt[c.tq], dst, c.pitch);
+                  idct(coef, c.tq, dst, c.pitch);
                 }
               }
             }
         }
         if (restart) until_restart--;
       }
-    // position after the entropy-coded segment: the next marker
-    const uint8_t* q = br.p;
-    if (br.hit_marker) { /* p points at the 0xFF of the marker */ }
-    while (q + 1 < d + n && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
-    p = q;
+    p = ent.after();  // position after the entropy-coded segment: the next marker
     return true;
   }
 
@@ -324,8 +548,9 @@ struct Jpeg {
   // AC scans carry one component and walk its own blocks; first passes (Ah == 0) write coefficient << Al, refinement passes add one
   // bit of precision to what is already there.
   bool scan_progressive(const uint8_t*& p, const std::vector<int>& sc, int Ss, int Se, int Ah, int Al) {
+    ent.start(p, d + n);
     BitReader br;
-    br.p = p; br.end = d + n;
+    br.open(ent);
     for (int ci : sc) comp[ci].pred = 0;
     const int mcux = (W + 8 * hmax - 1) / (8 * hmax), mcuy = (H + 8 * vmax - 1) / (8 * vmax);
     const bool inter = sc.size() > 1;
@@ -337,11 +562,8 @@ struct Jpeg {
     for (int my = 0; my < uy; my++)
       for (int mx = 0; mx < ux; mx++) {
         if (restart && until_restart == 0) {
-          br.reset();
-          const uint8_t* q = br.p;
-          while (q + 1 < d + n && !(q[0] == 0xFF && q[1] >= 0xD0 && q[1] <= 0xD7)) q++;
-          if (q + 1 >= d + n) { err = "missing restart marker"; return false; }
-          br.p = q + 2;
+          if (!ent.next_restart()) { err = "missing restart marker"; return false; }
+          br.open(ent);
           for (int ci : sc) comp[ci].pred = 0;
           eobrun = 0;
           until_restart = restart;
@@ -426,9 +648,7 @@ struct Jpeg {
         }
         if (restart) until_restart--;
       }
-    const uint8_t* q = br.p;
-    while (q + 1 < d + n && !(q[0] == 0xFF && q[1] != 0x00 && !(q[1] >= 0xD0 && q[1] <= 0xD7))) q++;
-    p = q;
+    p = ent.after();
     return true;
   }
 
@@ -460,6 +680,11 @@ struct Jpeg {
             s += pq ? 2 : 1;
           }
           qt_set[tq] = true;
+          qt_small[tq] = true;
+          for (int i = 0; i < 64; i++) {
+            qt16[tq][i] = (int16_t)(qt[tq][i] <= 255 ? qt[tq][i] : 0);
+            if (qt[tq][i] > 255) qt_small[tq] = false;
+          }
         }
       } else if (m == 0xC4) {  // DHT
         while (s < se) {
@@ -547,7 +772,7 @@ struct Jpeg {
         if (!c.needed) continue;
         for (int Y = 0; Y < c.bh; Y++)
           for (int X = 0; X < c.bw; X++)
-            idct_islow(c.coefs.data() + ((size_t)Y * c.bw + X) * 64, qt[c.tq], c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8, c.pitch);
+            idct(c.coefs.data() + ((size_t)Y * c.bw + X) * 64, c.tq, c.plane.data() + ((size_t)Y * 8) * c.pitch + (size_t)X * 8, c.pitch);
       }
     return true;
   }
@@ -563,40 +788,17 @@ struct Jpeg {
     if (exact && hx == 1 && vx == 1) { memcpy(dst, row(y), W); return; }
     const bool fancy = n > 2;
     if (exact && fancy && hx == 2 && vx == 1) {  // h2v1_fancy_upsample
-      const uint8_t* __restrict__ in = row(y);
-      dst[0] = in[0];
-      dst[1] = (uint8_t)((in[0] * 3 + in[1] + 2) >> 2);
-      for (int i = 1; i < n - 1; i++) {
-        const int v = in[i] * 3;
-        dst[2 * i] = (uint8_t)((v + in[i - 1] + 1) >> 2);
-        dst[2 * i + 1] = (uint8_t)((v + in[i + 1] + 2) >> 2);
-      }
-      dst[2 * n - 2] = (uint8_t)((in[n - 1] * 3 + in[n - 2] + 1) >> 2);
-      dst[2 * n - 1] = in[n - 1];
+      h2v1_fancy_row(row(y), dst, n);
       return;
     }
     if (exact && fancy && hx == 2 && vx == 2) {  // h2v2_fancy_upsample
       const int r = y >> 1;
-      const uint8_t* __restrict__ in0 = row(r);
-      const uint8_t* __restrict__ in1 = row((y & 1) ? r + 1 : r - 1);
-      dst[0] = (uint8_t)(((in0[0] * 3 + in1[0]) * 4 + 8) >> 4);
-      dst[1] = (uint8_t)(((in0[0] * 3 + in1[0]) * 3 + (in0[1] * 3 + in1[1]) + 7) >> 4);
-      for (int i = 1; i < n - 1; i++) {  // column sums recomputed per column: independent iterations (vectorisable)
-        const int last = in0[i - 1] * 3 + in1[i - 1], cur = in0[i] * 3 + in1[i], next = in0[i + 1] * 3 + in1[i + 1];
-        dst[2 * i] = (uint8_t)((cur * 3 + last + 8) >> 4);
-        dst[2 * i + 1] = (uint8_t)((cur * 3 + next + 7) >> 4);
-      }
-      const int cur = in0[n - 1] * 3 + in1[n - 1], last = in0[n - 2] * 3 + in1[n - 2];
-      dst[2 * n - 2] = (uint8_t)((cur * 3 + last + 8) >> 4);
-      dst[2 * n - 1] = (uint8_t)((cur * 4 + 7) >> 4);
+      h2v2_fancy_row(row(r), row((y & 1) ? r + 1 : r - 1), dst, n);
       return;
     }
     if (exact && hx == 1 && vx == 2) {  // h1v2_fancy_upsample (libjpeg-turbo; no width condition)
       const int r = y >> 1;
-      const uint8_t* __restrict__ in0 = row(r);
-      const uint8_t* __restrict__ in1 = row((y & 1) ? r + 1 : r - 1);
-      const int bias = (y & 1) ? 2 : 1;
-      for (int x = 0; x < W; x++) dst[x] = (uint8_t)((in0[x] * 3 + in1[x] + bias) >> 2);
+      h1v2_fancy_row(row(r), row((y & 1) ? r + 1 : r - 1), dst, W, (y & 1) ? 2 : 1);
       return;
     }
     // replication (int_upsample / h2v1_upsample / h2v2_upsample); non-integral ratios are approximated the same way
@@ -608,6 +810,13 @@ struct Jpeg {
     }
   }
 
+  // full-resolution row y of a component: the plane's own row when it is not subsampled, else upsampled into `tmp`
+  const uint8_t* full_row(const Comp& c, int y, uint8_t* tmp) const {
+    if (c.h == hmax && c.v == vmax) return c.plane.data() + (size_t)(y < c.dh ? y : c.dh - 1) * c.pitch;
+    upsample_row(c, y, tmp);
+    return tmp;
+  }
+
   bool to_mat(Mat& out, bool gray) {
     const bool rgb_coded = nc == 3 && ((adobe && adobe_transform == 0) || (!adobe && comp[0].id == 'R' && comp[1].id == 'G' && comp[2].id == 'B'));
     size_t line_len = (size_t)W + 8;
@@ -617,39 +826,27 @@ struct Jpeg {
     if (gray) {
       if (rgb_coded) { err = "grey output of an RGB-coded JPEG is not supported"; return false; }
       out.create(H, W, SB_8UC1);
-      for (int y = 0; y < H; y++) {  // luma is never subsampled in practice; handled anyway
-        upsample_row(comp[0], y, ln[0]);
-        memcpy(out.ptr<uint8_t>(y), ln[0], W);
-      }
+      for (int y = 0; y < H; y++)  // luma is never subsampled in practice; handled anyway
+        memcpy(out.ptr<uint8_t>(y), full_row(comp[0], y, ln[0]), W);
       return true;
     }
     out.create(H, W, SB_8UC3);
     for (int y = 0; y < H; y++) {
       uint8_t* __restrict__ o = out.ptr<uint8_t>(y);
-      for (int i = 0; i < nc; i++) upsample_row(comp[i], y, ln[i]);
-      const uint8_t* __restrict__ p0 = ln[0];
+      const uint8_t* src[3] = {nullptr, nullptr, nullptr};
+      for (int i = 0; i < nc; i++) src[i] = full_row(comp[i], y, ln[i]);
+      const uint8_t* __restrict__ p0 = src[0];
       if (nc == 1) {
-        for (int x = 0; x < W; x++) o[3 * x] = o[3 * x + 1] = o[3 * x + 2] = p0[x];
+        grey_to_bgr_row(p0, o, W);
         continue;
       }
-      const uint8_t* __restrict__ p1 = ln[1];
-      const uint8_t* __restrict__ p2 = ln[2];
+      const uint8_t* __restrict__ p1 = src[1];
+      const uint8_t* __restrict__ p2 = src[2];
       if (rgb_coded) {
         for (int x = 0; x < W; x++) { o[3 * x] = p2[x]; o[3 * x + 1] = p1[x]; o[3 * x + 2] = p0[x]; }
         continue;
       }
-      // jdcolor.c ycc_rgb_convert, SCALEBITS 16: the table entries written out as arithmetic (FIX(1.40200) = 91881,
-      // FIX(1.77200) = 116130, FIX(0.71414) = 46802, FIX(0.34414) = 22554, ONE_HALF = 32768; arithmetic right shifts)
-      for (int x = 0; x < W; x++) {
-        const int yy = p0[x], cb = p1[x] - 128, cr = p2[x] - 128;
-        int r = yy + ((91881 * cr + 32768) >> 16);
-        int g = yy + ((-22554 * cb + 32768 - 46802 * cr) >> 16);
-        int b = yy + ((116130 * cb + 32768) >> 16);
-        r = r < 0 ? 0 : (r > 255 ? 255 : r);
-        g = g < 0 ? 0 : (g > 255 ? 255 : g);
-        b = b < 0 ? 0 : (b > 255 ? 255 : b);
-        o[3 * x] = (uint8_t)b; o[3 * x + 1] = (uint8_t)g; o[3 * x + 2] = (uint8_t)r;
-      }
+      ycc_to_bgr_row(p0, p1, p2, o, W);
     }
     return true;
   }
