@@ -89,6 +89,55 @@ def test_jpeg_matches_opencv(cli, tmp_path):
     assert n == 42
 
 
+def test_simd_and_scalar_inverse_dct_agree(cli, tmp_path):
+    """The SSE2 inverse DCT is taken only for blocks whose sum |coef * q| proves that its 16-bit lanes cannot overflow; the rest
+    go through the 64-bit scalar transform.  Files with both kinds of blocks (full-swing checkerboards and noise at quality
+    100) decode to OpenCV's bytes, and to the same bytes when SB200_JPEG_SCALAR=1 forces the scalar transform everywhere."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(23)
+    y, x = np.mgrid[0:64, 0:96]
+    imgs = [np.repeat((((x + y) & 1) * 255).astype(np.uint8)[..., None], 3, -1), np.repeat((((x // 3 + y // 5) & 1) * 255).astype(np.uint8)[..., None], 3, -1),
+            rng.integers(0, 2, (64, 96, 3), dtype=np.uint8) * 255, rng.integers(0, 256, (64, 96, 3), dtype=np.uint8), _texture(64, 96, rng)]
+    for k, img in enumerate(imgs):
+        for q, sf in [(100, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444), (100, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420), (92, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420)]:
+            ok, b = cv2.imencode(".jpg", img, [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, sf])
+            assert ok
+            _check_against_cv2(cli, tmp_path, b.tobytes(), ("simd/scalar", k, q, hex(sf)))
+            p = str(tmp_path / "t.bin")
+            fast, _ = decode(cli, p, str(tmp_path / "f.pnm"), False)
+            os.environ["SB200_JPEG_SCALAR"] = "1"
+            try:
+                slow, _ = decode(cli, p, str(tmp_path / "s.pnm"), False)
+            finally:
+                del os.environ["SB200_JPEG_SCALAR"]
+            assert fast is not None and slow is not None and np.array_equal(fast, slow), (k, q, hex(sf))
+    # valid 8-bit files stay inside the guard; blown-up quantisation tables push blocks to and over it (not compared with
+    # OpenCV: libjpeg-turbo's own SIMD transform wraps there)
+    ok, b = cv2.imencode(".jpg", imgs[3], [cv2.IMWRITE_JPEG_QUALITY, 60])
+    data = bytearray(b.tobytes())
+    for scale in (6, 8, 9, 10, 12, 40, 255):
+        d2, i = bytearray(data), 2
+        while i + 4 <= len(d2) and d2[i] == 0xFF and d2[i + 1] != 0xDA:
+            seg = (d2[i + 2] << 8) | d2[i + 3]
+            if d2[i + 1] == 0xDB:
+                j = i + 4
+                while j < i + 2 + seg:
+                    assert d2[j] >> 4 == 0
+                    for t in range(64):
+                        d2[j + 1 + t] = min(255, max(1, (d2[j + 1 + t] * scale) // 4))
+                    j += 65
+            i += 2 + seg
+        p = str(tmp_path / "big_q.jpg")
+        open(p, "wb").write(bytes(d2))
+        fast, _ = decode(cli, p, str(tmp_path / "f.pnm"), False)
+        os.environ["SB200_JPEG_SCALAR"] = "1"
+        try:
+            slow, _ = decode(cli, p, str(tmp_path / "s.pnm"), False)
+        finally:
+            del os.environ["SB200_JPEG_SCALAR"]
+        assert fast is not None and slow is not None and np.array_equal(fast, slow), scale
+
+
 def test_progressive_jpeg_matches_opencv(cli, tmp_path):
     """SOF2 files (spectral selection + successive approximation: libjpeg's standard script exercises DC / AC first and
     refinement scans), with restart intervals and every chroma layout."""
