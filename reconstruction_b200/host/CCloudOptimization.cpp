@@ -4,6 +4,8 @@
 #include <stdlib.h>
 #include <sys/stat.h>
 
+#include <new>
+
 #include "../../include/stereo_b200.h"
 
 void CCloudOptimization::Init(int sor_meank, double sor_stdThres, int sor_meank1, double sor_stdThres1, double mls_radius,
@@ -39,7 +41,58 @@ void CCloudOptimization::InsertPoints(const double* p, const unsigned char* c, s
   else bgr.insert(bgr.end(), 3 * n, (unsigned char)0);
 }
 
-bool CCloudOptimization::FilterPoints(int idx, int device, const double* p, size_t n, std::vector<float>& rec, size_t& kept, double stats[5],
+void CCloudOptimization::Reserve(size_t more) {
+  try {
+    xyz.reserve(xyz.size() + 3 * more);
+    bgr.reserve(bgr.size() + 3 * more);
+    if (sink_enabled) normals.reserve(normals.size() + 7 * more);  // at most every point is kept
+  } catch (const std::bad_alloc&) {
+  }
+}
+
+CCloudOptimization::~CCloudOptimization() {
+  FlushFilterPly();
+  {
+    std::lock_guard<std::mutex> lk(ply_mu_);
+    ply_stop_ = true;
+  }
+  ply_cv_.notify_all();
+  if (ply_thread_.joinable()) ply_thread_.join();
+}
+
+void CCloudOptimization::QueueFilterPly(SinkRecords&& rec, size_t kept) {
+  std::lock_guard<std::mutex> lk(ply_mu_);
+  ply_pending_ = std::move(rec);  // supersedes records that were still waiting
+  ply_pending_kept_ = kept;
+  ply_have_ = true;
+  if (!ply_thread_.joinable())
+    ply_thread_ = std::thread([this]() {
+      std::unique_lock<std::mutex> lk(ply_mu_);
+      for (;;) {
+        ply_cv_.wait(lk, [this] { return ply_have_ || ply_stop_; });
+        if (!ply_have_) return;
+        SinkRecords rec = std::move(ply_pending_);
+        const size_t kept = ply_pending_kept_;
+        ply_pending_ = SinkRecords();
+        ply_have_ = false;
+        ply_writing_ = true;
+        lk.unlock();
+        if (!WritePlyPointNormal("tmp/cloud_filter.ply", rec.data(), kept)) printf("cannot write tmp/cloud_filter.ply\n");
+        rec = SinkRecords();
+        lk.lock();
+        ply_writing_ = false;
+        ply_idle_.notify_all();
+      }
+    });
+  ply_cv_.notify_all();
+}
+
+void CCloudOptimization::FlushFilterPly() {
+  std::unique_lock<std::mutex> lk(ply_mu_);
+  ply_idle_.wait(lk, [this] { return !ply_have_ && !ply_writing_; });
+}
+
+bool CCloudOptimization::FilterPoints(int idx, int device, const double* p, size_t n, SinkRecords& rec, size_t& kept, double stats[5],
                                       std::string& err) const {
   kept = 0;
   if (n == 0) return true;
@@ -60,7 +113,7 @@ bool CCloudOptimization::FilterPoints(int idx, int device, const double* p, size
   return true;
 }
 
-void CCloudOptimization::StoreFiltered(int idx, std::vector<float>&& rec, size_t kept, const double stats[5]) {
+void CCloudOptimization::StoreFiltered(int idx, SinkRecords&& rec, size_t kept, const double stats[5]) {
   std::lock_guard<std::mutex> lk(ready_mu_);
   Ready& r = ready_[idx];
   r.rec = std::move(rec);
@@ -75,7 +128,7 @@ void CCloudOptimization::filter(int idx) {
   pair_begin.push_back(open_begin_);
   if (!sink_enabled || end <= begin) { kept_per_pair.push_back(0); return; }
   printf("Initial points: %zu\n", end - begin);
-  std::vector<float> rec;
+  SinkRecords rec;
   size_t kept = 0;
   double stats[5] = {0, 0, 0, 0, 0};
   bool have = false;
@@ -104,7 +157,7 @@ void CCloudOptimization::filter(int idx) {
          stats[1], stats[2], stats[3]);
   normals.insert(normals.end(), rec.begin(), rec.begin() + 7 * kept);  // *cloud_normals += *cloud_normal (:117)
   kept_per_pair.push_back(kept);
-  WritePlyPointNormal("tmp/cloud_filter.ply", rec.data(), kept);  // :119 (the mesher's input)
+  QueueFilterPly(std::move(rec), kept);  // :119 (the mesher's input)
 }
 
 bool WritePlyPointNormal(const std::string& path, const float* rec7, size_t n) {
@@ -143,6 +196,7 @@ bool WritePlyF32(const std::string& path, const double* xyz, const unsigned char
 }
 
 void CCloudOptimization::run() {
+  FlushFilterPly();
   if (!m_ImageData || m_ImageData->outfilename.empty()) return;
   const size_t n = xyz.size() / 3;
   if (WritePlyF32(m_ImageData->outfilename, xyz.data(), bgr.data(), n))

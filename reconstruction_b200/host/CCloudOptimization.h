@@ -7,15 +7,34 @@
 // stitching: external Windows executables) is out of scope.
 #pragma once
 #include <stdint.h>
+#include <condition_variable>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "CManageData.h"
 
+// std::allocator whose construct() default-initialises: resize() of a vector of doubles / floats / bytes allocates without
+// touching the pages.  The per-pair point buffers are sized for the worst case (one point per pixel, 302 MB of doubles at
+// 4096x3072) before the pair is matched; value-initialising them would touch every page (more host time than the GPU spends on
+// the pair), this way only the rows the device copy writes are ever touched.
+template <class T>
+struct UninitAllocator : std::allocator<T> {
+  template <class U> struct rebind { using other = UninitAllocator<U>; };
+  template <class U, class... A> void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+typedef std::vector<float, UninitAllocator<float>> SinkRecords;  // 7 floats per kept point: x y z nx ny nz curvature
+
 class CCloudOptimization {
  public:
+  CCloudOptimization() = default;
+  ~CCloudOptimization();
   void Init(int sor_meank, double sor_stdThres, int sor_meank1, double sor_stdThres1, double mls_radius, CManageData* m_data,
             bool isdelete_);
   void InsertPoint(sbcv::Mat p);  // 3x1 f64 (CCloudOptimization.cpp:59-62)
@@ -25,9 +44,16 @@ class CCloudOptimization {
   // The GPU part of filter(idx) on its own (thread-safe, const): outlier removal + normals + orientation of n points of pair idx
   // on `device`.  The matcher's workers call it right after a pair's triangulation — while other pairs are still matching — and
   // hand the result over with StoreFiltered(); filter(idx) then only appends it (same records, same order, same files).
-  bool FilterPoints(int idx, int device, const double* xyz, size_t n, std::vector<float>& rec7, size_t& kept, double stats5[5],
+  bool FilterPoints(int idx, int device, const double* xyz, size_t n, SinkRecords& rec7, size_t& kept, double stats5[5],
                     std::string& err) const;
-  void StoreFiltered(int idx, std::vector<float>&& rec7, size_t kept, const double stats5[5]);
+  void StoreFiltered(int idx, SinkRecords&& rec7, size_t kept, const double stats5[5]);
+  // the matcher knows how many points all pairs hold before it hands the first one over: size the merged buffers once
+  // (address space only; a refused reservation is not an error, the vectors then grow as before)
+  void Reserve(size_t more_points);
+  // tmp/cloud_filter.ply is rewritten by every filter() call (:119) and only its last state is ever read: a background thread
+  // writes the newest records handed to it and drops the ones a newer pair superseded meanwhile.  Flush waits for the file
+  // to hold the last pair's records (run() and the destructor call it).
+  void FlushFilterPly();
   void run();            // writes <outfilename> (binary little-endian PLY: float xyz, uchar b g r) and <outfilename>.normals.ply
 
   // what the sink holds after the matcher ran
@@ -52,9 +78,16 @@ class CCloudOptimization {
   bool isdelete = false;
   CManageData* m_ImageData = nullptr;
   size_t open_begin_ = 0;
-  struct Ready { std::vector<float> rec; size_t kept = 0; double stats[5] = {0, 0, 0, 0, 0}; };
+  struct Ready { SinkRecords rec; size_t kept = 0; double stats[5] = {0, 0, 0, 0, 0}; };
   std::map<int, Ready> ready_;  // pairs filtered ahead of filter(idx)
   std::mutex ready_mu_;
+  void QueueFilterPly(SinkRecords&& rec7, size_t kept);
+  std::thread ply_thread_;
+  std::mutex ply_mu_;
+  std::condition_variable ply_cv_, ply_idle_;
+  SinkRecords ply_pending_;
+  size_t ply_pending_kept_ = 0;
+  bool ply_have_ = false, ply_writing_ = false, ply_stop_ = false;
 };
 
 // cloud<idx>.ply as DisparityToCloud writes it when isoutput is set (CStereoMatching.cpp:707-730,753-757)

@@ -5,22 +5,13 @@
 #include <string.h>
 
 #include <chrono>
+#include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <utility>
 
 #include "../../include/stereo_b200.h"
-
-// std::allocator that leaves trivially constructible elements uninitialised: the point buffers are sized for the worst case
-// (one point per pixel, 302 MB of doubles at 4096x3072) before the pair is matched; value-initialising them would touch every page
-// (more host time than the GPU spends on the pair), this way only the rows the device copy writes are ever touched.
-template <class T>
-struct UninitAllocator : std::allocator<T> {
-  template <class U> struct rebind { using other = UninitAllocator<U>; };
-  template <class U, class... A> void construct(U* p, A&&... a) {
-    if constexpr (sizeof...(A) == 0) ::new ((void*)p) U; else ::new ((void*)p) U(std::forward<A>(a)...);
-  }
-};
 
 struct CStereoMatching::PairResult {
   bool ok = false;
@@ -185,7 +176,7 @@ bool CStereoMatching::RunPair(sb200_ctx* ctx, int device, int CamPair, PairResul
   // the sink's per-pair filter (outlier removal, normals, orientation) on this worker's device, now, while other pairs are
   // still matching; CCloudOptimization::filter(CamPair) appends the stored result when the pairs are handed over in order
   if (!keep_on_device && m_CloudOptimization && m_CloudOptimization->sink_enabled && r.n > 0) {
-    std::vector<float> rec;
+    SinkRecords rec;
     size_t kept = 0;
     double stats[5] = {0, 0, 0, 0, 0};
     std::string err;
@@ -247,6 +238,35 @@ bool CStereoMatching::GatherPairs(std::vector<sb200_ctx*>& ctxs, const std::vect
         }
       }
     });
+  // The sink's per-pair filter runs ahead of the ordered hand-over here too: one host thread per device takes the pairs as the
+  // collector below receives them and leaves the records with StoreFiltered(); filter(pair) then only appends them.
+  std::mutex fq_mu;
+  std::condition_variable fq_cv;
+  std::deque<int> fq;
+  bool fq_done = false;
+  std::vector<std::thread> filterers;
+  if (m_CloudOptimization && m_CloudOptimization->sink_enabled)
+    for (int d = 0; d < n_dev; d++)
+      filterers.emplace_back([&, d]() {
+        for (;;) {
+          int p;
+          {
+            std::unique_lock<std::mutex> lk(fq_mu);
+            fq_cv.wait(lk, [&] { return fq_done || !fq.empty(); });
+            if (fq.empty()) return;
+            p = fq.front();
+            fq.pop_front();
+          }
+          PairResult& r = results[p];
+          SinkRecords rec;
+          size_t kept = 0;
+          double stats[5] = {0, 0, 0, 0, 0};
+          std::string err;
+          if (m_CloudOptimization->FilterPoints(p, ctx_dev[d], r.xyz.data(), (size_t)r.n, rec, kept, stats, err))
+            m_CloudOptimization->StoreFiltered(p, std::move(rec), kept, stats);
+          // on failure filter(p) retries on the sink's own device and reports
+        }
+      });
   // collector: device 0's gathered buffers, ticket by ticket, split into the pairs by the gathered counts
   const bool want_bgr = m_data->isoutput != 0;
   std::vector<int64_t> counts(n_dev);
@@ -273,11 +293,18 @@ bool CStereoMatching::GatherPairs(std::vector<sb200_ctx*>& ctxs, const std::vect
         results[p].xyz.assign(xyz.begin() + 3 * off, xyz.begin() + 3 * (off + n));
         if (want_bgr) results[p].bgr.assign(bgr.begin() + 3 * off, bgr.begin() + 3 * (off + n));
         results[p].n = (int64_t)n;
+        if (!filterers.empty() && n > 0) {
+          { std::lock_guard<std::mutex> lk(fq_mu); fq.push_back((int)p); }
+          fq_cv.notify_one();
+        }
       }
       off += n;
     }
   }
   for (auto& w : workers) w.join();
+  { std::lock_guard<std::mutex> lk(fq_mu); fq_done = true; }
+  fq_cv.notify_all();
+  for (auto& f : filterers) f.join();
   double ms = 0;
   int64_t bytes = 0, nx = 0;
   sb200_comm_stats(comms[0], &ms, &bytes, &nx, 0);
@@ -371,14 +398,15 @@ void CStereoMatching::MatchAllLayer() {
     if (!req.empty() && nt > 0) prefetcher.start(req, nt);
   }
   prefetch_ = &prefetcher;
-  if (G == 1) {
+  // 0 = off, 1 = with several devices (default), 2 = always (one device too: the same path end to end, for tests on a one-GPU box)
+  const int gather_mode = allgather >= 0 ? allgather : (getenv("SB200_ALLGATHER") ? atoi(getenv("SB200_ALLGATHER")) : 1);
+  if ((gather_mode == 2 || (gather_mode == 1 && n_dev > 1 && G > 1)) && GatherPairs(ctxs, ctx_dev, n_dev, results)) {
+    // the points of every pair reached the host through ONE path, the NCCL all-gather of the C ABI
+  } else if (G == 1) {
     for (int p = 0; p < P; p++) {
       printf("processing pair %d: cam %d and cam %d...\n", p + 1, m_data->cam[p][0].camID, m_data->cam[p][1].camID);
       RunPair(ctxs[0], ctx_dev[0], p, results[p]);
     }
-  } else if (n_dev > 1 && (allgather >= 0 ? allgather != 0 : !(getenv("SB200_ALLGATHER") && atoi(getenv("SB200_ALLGATHER")) == 0)) &&
-             GatherPairs(ctxs, ctx_dev, n_dev, results)) {
-    // several devices: the points of every pair reached the host through ONE path, the NCCL all-gather of the C ABI
   } else {  // pair p -> context p mod G, context j on device j mod n_dev; each worker owns its context
     std::mutex io;
     std::vector<std::thread> workers;
@@ -394,6 +422,12 @@ void CStereoMatching::MatchAllLayer() {
   prefetch_ = nullptr;
   gpu_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   // hand the results to the sink in pair order: InsertPoint per point, then filter(pair) (:29-31,751)
+  if (m_CloudOptimization) {
+    size_t total = 0;
+    for (int p = 0; p < P; p++)
+      if (results[p].ok) total += (size_t)results[p].n;
+    m_CloudOptimization->Reserve(total);
+  }
   for (int p = 0; p < P; p++) {
     PairResult& r = results[p];
     if (!r.ok) {

@@ -31,7 +31,8 @@ class CStereoMatching {
   std::vector<int> devices;        // CUDA devices to use; empty = SB200_DEVICES or every visible device
   int contexts_per_device = 0;     // camera pairs in flight per device; <= 0 = SB200_CTX_PER_DEVICE or 3
   int allgather = -1;              // several devices: collect the per-pair point buffers with the NCCL all-gather of the C ABI
-                                   // (sb200_exchange_*) instead of one device-to-host copy per worker; < 0 = SB200_ALLGATHER or on
+                                   // (sb200_exchange_*) instead of one device-to-host copy per worker; < 0 = SB200_ALLGATHER or 1;
+                                   // 2 = take that path with a single device too
   int decode_threads = 0;          // host threads decoding the input files ahead of the GPU; <= 0 = SB200_DECODE_THREADS or the core count (max 16)
   int last_status = 0;             // sb200 status of the last failing call, 0 if none
   std::string last_error;

@@ -99,6 +99,39 @@ def test_cli_reads_the_references_image_formats(tmp_path, golden_dir, fmt):
     assert np.array_equal(bgr, pbgr)
 
 
+def test_cli_gather_path_on_one_gpu(tmp_path):
+    """SB200_ALLGATHER=2 takes the several-device path with a single device (a one-rank communicator, the workers' points kept in
+    HBM, the exchange thread, the sink filter running ahead on its own host thread): raw clouds, merged cloud, oriented cloud and
+    tmp/cloud_filter.ply must equal the default path's, byte for byte."""
+    capi.build()
+    subprocess.run(["make", "-s", "-C", HOST], check=True)
+    L, w0, h0, n_pairs = 3, 64, 48, 5
+    outs = {}
+    for tag, env in (("plain", {"SB200_DEVICES": "0", "SB200_ALLGATHER": "0"}), ("gather", {"SB200_DEVICES": "0", "SB200_ALLGATHER": "2", "SB200_CTX_PER_DEVICE": "2"}),
+                     ("gather1", {"SB200_DEVICES": "0", "SB200_ALLGATHER": "2", "SB200_CTX_PER_DEVICE": "1"})):
+        d = tmp_path / tag
+        d.mkdir()
+        cfg, _ = stage.write_dataset(str(d), L, w0, h0, n_pairs=n_pairs, isoutput=1)
+        r = subprocess.run([os.path.join(HOST, "reconstruction"), cfg], cwd=str(d), capture_output=True, text=True, env=dict(os.environ, **env))
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert ("point all-gather:" in r.stdout) == (tag != "plain"), r.stdout
+        files = [f"cloud{p}.ply" for p in range(n_pairs)] + ["out.ply", "out.ply.normals.ply", os.path.join("tmp", "cloud_filter.ply")]
+        outs[tag] = {f: open(d / f, "rb").read() for f in files}
+        assert all(len(v) > 200 for v in outs[tag].values())
+    def records(raw):  # PointNormal PLY: 7 float32 per vertex after the header
+        body = raw[raw.index(b"end_header\n") + 11:]
+        return np.frombuffer(body, np.float32).reshape(-1, 7)
+
+    for f in outs["plain"]:
+        for other in ("gather", "gather1"):
+            if f.startswith("cloud") or f == "out.ply":
+                assert outs["plain"][f] == outs[other][f], (f, other)
+            else:  # kept points identical; normals are eigenvectors (same code, same inputs - compared numerically all the same)
+                a, b = records(outs["plain"][f]), records(outs[other][f])
+                assert a.shape == b.shape and len(a) > 0 and np.array_equal(a[:, :3].view(np.int32), b[:, :3].view(np.int32)), (f, other)
+                assert np.allclose(a[:, 3:], b[:, 3:], rtol=1e-4, atol=1e-5, equal_nan=True), (f, other)
+
+
 def test_cli_two_gpus_gathers_the_points_over_nccl(tmp_path):
     """Several devices: the workers keep their points in HBM and the C ABI's NCCL all-gather (sb200_exchange_*) collects them;
     the merged cloud must equal the single-device run's, byte for byte (pair order, CloudOptimization/CCloudOptimization.cpp:123)."""
