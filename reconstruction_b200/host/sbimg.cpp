@@ -908,34 +908,66 @@ bool png_decode(const uint8_t* d, size_t n, Mat& out, bool gray, std::string& er
     inflateEnd(&zs);
     if ((rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) || got != raw.size()) { err = "PNG data does not inflate to the image size"; return false; }
   }
+  const bool colour_src = ctype == 2 || ctype == 6 || ctype == 3;
+  // 8-bit grey / grey+alpha / RGB / RGBA without interlace (what cameras and OpenCV write): rows go from the unfiltered scanline
+  // straight to the output.  Everything else is expanded to 16-bit RGBA samples first (px) and converted below.
+  const bool direct = !interlace && depth == 8 && ctype != 3;
+  if (direct) out.create((int)H, (int)W, gray ? SB_8UC1 : SB_8UC3);
   // sample (x, y, channel) as 8-bit after the conversions OpenCV asks libpng for
-  std::vector<uint16_t> px((size_t)W * H * 4, 255);  // RGBA, full sample width (alpha unused)
+  std::vector<uint16_t> px;
+  if (!direct) px.assign((size_t)W * H * 4, 255);  // RGBA, full sample width (alpha unused)
   size_t off = 0;
   for (int ps = 0; ps < npass; ps++) {
     if (!pw[ps] || !ph[ps]) continue;
     const size_t rb = row_bytes(pw[ps]);
-    std::vector<uint8_t> prev(rb, 0);
+    const std::vector<uint8_t> zero_row(rb, 0);
     for (uint32_t y = 0; y < ph[ps]; y++) {
       const int ft = raw[off];
-      uint8_t* cur = raw.data() + off + 1;
-      for (size_t i = 0; i < rb; i++) {
-        const int a = i >= (size_t)bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= (size_t)bpp ? prev[i - bpp] : 0;
-        int pred = 0;
-        switch (ft) {
-          case 0: break;
-          case 1: pred = a; break;
-          case 2: pred = b; break;
-          case 3: pred = (a + b) >> 1; break;
-          case 4: {
+      uint8_t* __restrict__ cur = raw.data() + off + 1;
+      const uint8_t* __restrict__ prev = y ? cur - (rb + 1) : zero_row.data();  // the row above, already unfiltered in place
+      const size_t B = (size_t)bpp;
+      switch (ft) {
+        case 0: break;
+        case 1:
+          for (size_t i = B; i < rb; i++) cur[i] = (uint8_t)(cur[i] + cur[i - B]);
+          break;
+        case 2:
+          for (size_t i = 0; i < rb; i++) cur[i] = (uint8_t)(cur[i] + prev[i]);
+          break;
+        case 3:
+          for (size_t i = 0; i < B && i < rb; i++) cur[i] = (uint8_t)(cur[i] + (prev[i] >> 1));
+          for (size_t i = B; i < rb; i++) cur[i] = (uint8_t)(cur[i] + ((cur[i - B] + prev[i]) >> 1));
+          break;
+        case 4:
+          for (size_t i = 0; i < B && i < rb; i++) cur[i] = (uint8_t)(cur[i] + prev[i]);  // a = c = 0: the predictor is b
+          for (size_t i = B; i < rb; i++) {
+            const int a = cur[i - B], b = prev[i], c = prev[i - B];
             const int pp = a + b - c, pa = abs(pp - a), pb = abs(pp - b), pc = abs(pp - c);
-            pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
-            break;
+            cur[i] = (uint8_t)(cur[i] + ((pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c)));
           }
-          default: err = "bad PNG filter"; return false;
-        }
-        cur[i] = (uint8_t)(cur[i] + pred);
+          break;
+        default: err = "bad PNG filter"; return false;
       }
-      memcpy(prev.data(), cur, rb);
+      if (direct) {
+        uint8_t* __restrict__ o = out.ptr<uint8_t>((int)y);
+        if (gray) {
+          if (ch == 1) memcpy(o, cur, W);
+          else if (ch == 2) { for (uint32_t x = 0; x < W; x++) o[x] = cur[2 * (size_t)x]; }
+          else
+            for (uint32_t x = 0; x < W; x++) {  // png_set_rgb_to_gray, see below
+              const long r = cur[(size_t)x * ch], g = cur[(size_t)x * ch + 1], b = cur[(size_t)x * ch + 2];
+              o[x] = (uint8_t)((r == g && g == b) ? r : (9797 * r + 19234 * g + 3737 * b) >> 15);
+            }
+        } else {
+          if (ch <= 2) { for (uint32_t x = 0; x < W; x++) o[3 * (size_t)x] = o[3 * (size_t)x + 1] = o[3 * (size_t)x + 2] = cur[(size_t)x * ch]; }
+          else
+            for (uint32_t x = 0; x < W; x++) {
+              o[3 * (size_t)x] = cur[(size_t)x * ch + 2]; o[3 * (size_t)x + 1] = cur[(size_t)x * ch + 1]; o[3 * (size_t)x + 2] = cur[(size_t)x * ch];
+            }
+        }
+        off += rb + 1;
+        continue;
+      }
       const uint32_t Y = interlace ? adam7[ps][1] + y * adam7[ps][3] : y;
       for (uint32_t x = 0; x < pw[ps]; x++) {
         const uint32_t X = interlace ? adam7[ps][0] + x * adam7[ps][2] : x;
@@ -960,7 +992,7 @@ bool png_decode(const uint8_t* d, size_t n, Mat& out, bool gray, std::string& er
       off += rb + 1;
     }
   }
-  const bool colour_src = ctype == 2 || ctype == 6 || ctype == 3;
+  if (direct) return true;
   if (gray) {
     out.create((int)H, (int)W, SB_8UC1);
     for (size_t i = 0; i < (size_t)W * H; i++) {
