@@ -108,3 +108,40 @@ def test_config_written_like_the_references_batch_tool(cli, tmp_path):
             K, Rt = cams[c["id"]]
             assert c["image"] == root + f"0001_Cam{c['id']}.jpg" and c["mask"] == root + f"mask/0001_Cam{c['id']}.jpg"
             assert np.array_equal(np.array(c["K"]).reshape(3, 3), K) and np.array_equal(np.array(c["Rt"]).reshape(3, 4), Rt)
+
+
+def _ply_body(path):
+    raw = open(path, "rb").read()
+    return raw[raw.index(b"end_header\n") + 11:]
+
+
+def test_sink_handover_without_a_gpu(tmp_path):
+    """The host mirror's sink around a stubbed sb200_sink_filter (tests/harness/sink_handover.cpp): records filtered ahead by
+    worker threads and records filtered inside filter() land in pair order; tmp/cloud_filter.ply - rewritten per pair by a
+    background thread that may drop superseded states - holds the LAST pair's records once run() returns; the merged files hold
+    every pair."""
+    import numpy as np
+
+    exe = str(tmp_path / "sink_handover")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-Wall", "-o", exe, os.path.join(os.path.dirname(os.path.abspath(__file__)), "harness", "sink_handover.cpp"),
+                    os.path.join(HOST, "CCloudOptimization.cpp"), os.path.join(HOST, "CManageData.cpp"), os.path.join(HOST, "sbcv.cpp"),
+                    os.path.join(HOST, "sbimg.cpp"), "-lz", "-lpthread"], check=True)
+    for counts in ([5, 0, 7, 300001, 4], [1000], [3, 3], [40000, 40001, 0]):
+        d = tmp_path / ("run" + "_".join(map(str, counts)))
+        d.mkdir()
+        r = subprocess.run([exe, str(d), str(len(counts))] + [str(c) for c in counts], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        expect = []
+        for p, n in enumerate(counts):
+            i = np.arange(n)
+            i = i[i % 3 != 0]
+            dev = 7.0 if p % 2 else 0.0
+            rec = np.stack([np.full(len(i), p), i, 0.25 * i + p, np.full(len(i), dev), i, np.full(len(i), n), np.ones(len(i))], 1).astype(np.float32)
+            expect.append(rec)
+        merged = np.frombuffer(_ply_body(d / "out.ply.normals.ply"), np.float32).reshape(-1, 7)
+        assert np.array_equal(merged, np.concatenate(expect)), counts
+        last = [e for e, n in zip(expect, counts) if n > 0][-1]  # filter() returns early for an empty pair (nothing is written for it)
+        got = np.frombuffer(_ply_body(d / "tmp" / "cloud_filter.ply"), np.float32).reshape(-1, 7)
+        assert np.array_equal(got, last), counts
+        assert len(_ply_body(d / "out.ply")) == 15 * sum(counts)
+        assert f"points {sum(counts)} kept {len(merged)}" in r.stdout, r.stdout
