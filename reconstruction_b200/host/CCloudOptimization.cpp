@@ -103,7 +103,7 @@ bool CCloudOptimization::FilterPoints(int idx, int device, const double* p, size
     for (int k = 0; k < 3; k++) cam[k] = m_ImageData->cam[idx][0].CamCenter.at<double>(k, 0);
   rec.resize(7 * n);
   // touch the pages before the device writes into them: a device-to-host copy into never-touched pageable memory faults them in
-  // inside the driver, measured 0.1 s per 7 M-point pair slower than faulting them here (profiles/r2_handover_ab_v1.json)
+  // inside the driver, measured 0.1 s per 7 M-point pair slower than faulting them here (profiles/r2_handover_ab_v1.json, _v2.json)
   memset(rec.data(), 0, sizeof(float) * 7 * n);
   int64_t k64 = 0;
   const int rc = sb200_sink_filter(device, p, (int64_t)n, m_sor_meank, m_sor_stdThres, m_mls_radius, cam, rec.data(), nullptr, (int64_t)n, &k64, stats);
